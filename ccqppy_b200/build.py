@@ -1,0 +1,43 @@
+"""Build the CUDA library in-tree: ccqppy_b200/csrc/libccqp_b200.so (sm_100a only).
+
+nvcc cross-compiles without a GPU, so this also is the "does it build" check
+(`__graft_entry__.build()`).  The .so is git-ignored but travels with the source tree."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(CSRC, "libccqp_b200.so")
+SOURCES = ["capi.cu"]
+HEADERS = ["common.cuh", "proj.cuh", "dense.cuh", "batched.cuh", os.path.join("..", "..", "include", "ccqp_b200.h")]
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              # the reference computes every scalar with separately rounded * and +; fused
+              # multiply-adds are written explicitly (fma()) where they are wanted
+              "-fmad=false",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+
+def _stale():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False, extra_flags=()):
+    """Compile if the library is missing or older than its sources.  Returns the library path."""
+    if not force and not _stale():
+        return LIB
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]
+    if verbose:
+        print(" ".join(cmd), file=sys.stderr)
+    subprocess.run(cmd, check=True, cwd=CSRC)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

@@ -1,0 +1,468 @@
+// C-ABI of the B200-native CCQP hot path (see include/ccqp_b200.h for the contract).
+// Host-side code only marshals: it uploads/borrows the Hessian shard, turns the block table into
+// the device projection tables, launches ONE persistent cooperative kernel per solve and copies
+// the result record back.  No algorithm runs on the CPU here.
+#include "../../include/ccqp_b200.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "batched.cuh"
+#include "dense.cuh"
+
+using namespace ccqp;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct ccqp_handle {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string last_error;
+    // matrix shard
+    const double* dA = nullptr;
+    DevBuf a_own;
+    long long n = 0, lda = 0, row0 = 0, nrows = 0;
+    // projection
+    bool have_proj = false;
+    long long proj_n = 0;
+    DevBuf lo, hi, ekind, bkind, boff, bdim, bpar, small_ids, big_ids;
+    int nblk = 0, nsmall = 0, nbig = 0, has_cone_ref = 0;
+    // workspaces
+    DevBuf work, partials, andparts, flags, out_dev, uniforms, batched_ws;
+    void* out_host = nullptr;   // pinned
+    long long npad = 0;
+    long long launches = 0;
+};
+
+namespace {
+
+const char* kStatusText[] = {
+    "ok", "invalid argument", "no CUDA device (this library has no CPU path)", "CUDA runtime error",
+    "unsupported request", "matrix or projection not set",
+    "Cone normal not implemented, yet.", "SPG consumed all supplied uniform samples",
+    "Range exceeds valid bounds", "device barrier timed out", "multi-GPU exchange error"};
+
+#define CU(h, call)                                                                  \
+    do {                                                                             \
+        cudaError_t e__ = (call);                                                    \
+        if (e__ != cudaSuccess) {                                                    \
+            (h)->last_error = std::string(#call) + ": " + cudaGetErrorString(e__);   \
+            return CCQP_ERR_CUDA;                                                    \
+        }                                                                            \
+    } while (0)
+
+long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
+
+ccqp_status copy_in(ccqp_handle* h, double* dst, const double* src, long long count, int memtype) {
+    CU(h, cudaMemcpyAsync(dst, src, (size_t)count * 8,
+                          memtype == CCQP_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+    return CCQP_OK;
+}
+ccqp_status copy_out(ccqp_handle* h, double* dst, const double* src, long long count, int memtype) {
+    CU(h, cudaMemcpyAsync(dst, src, (size_t)count * 8,
+                          memtype == CCQP_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream));
+    return CCQP_OK;
+}
+
+// slots of the work buffer (each npad doubles)
+enum { W_B = 0, W_X0, W_XOUT, W_HIN, W_HOUT, W_VEC0, W_COUNT = W_VEC0 + kNumVec };
+
+ccqp_status ensure_work(ccqp_handle* h) {
+    const long long npad = round_up(h->n, 64) + 64;
+    if (npad != h->npad || !h->work.p) {
+        CU(h, h->work.ensure((size_t)W_COUNT * npad * 8));
+        h->npad = npad;
+    }
+    CU(h, h->partials.ensure((size_t)2 * h->sm_count * kMaxRed * 8));
+    CU(h, h->andparts.ensure((size_t)2 * h->sm_count * 8));
+    CU(h, h->flags.ensure(64));
+    CU(h, h->out_dev.ensure(sizeof(DenseOut)));
+    if (!h->out_host) CU(h, cudaMallocHost(&h->out_host, 4096));
+    return CCQP_OK;
+}
+
+struct Tiling { int grid, CW, SW, np, nseg, rows_max; size_t smem; };
+
+Tiling choose_tiling(const ccqp_handle* h) {
+    Tiling t;
+    const long long n = h->n, nrows = h->nrows;
+    t.grid = (int)std::max(1LL, std::min<long long>(h->sm_count, nrows));
+    t.rows_max = (int)((nrows + t.grid - 1) / t.grid) + 1;
+    t.CW = (int)std::min<long long>(8192, round_up(n, 128));
+    t.SW = std::min(2048, t.CW);
+    for (;;) {
+        t.np = (int)((n + t.CW - 1) / t.CW);
+        const int spp_full = t.CW / t.SW;
+        const int last = (int)(n - (long long)(t.np - 1) * t.CW);
+        t.nseg = (t.np - 1) * spp_full + (last + t.SW - 1) / t.SW;
+        t.smem = dense_smem_bytes(t.CW, t.rows_max, t.nseg);
+        if (t.smem <= 200 * 1024 || t.SW >= t.CW) break;
+        t.SW *= 2;   // fewer, wider segments when a CTA owns many rows of a very wide matrix
+    }
+    return t;
+}
+
+void fill_ctx(ccqp_handle* h, DenseCtx& c, const Tiling& t) {
+    std::memset(&c, 0, sizeof(c));
+    double* w = h->work.as<double>();
+    c.A = h->dA; c.lda = h->lda; c.n = (int)h->n; c.row0 = (int)h->row0; c.nrows = (int)h->nrows;
+    c.aligned = ((reinterpret_cast<uintptr_t>(h->dA) & 31) == 0 && (h->lda % 4) == 0) ? 1 : 0;
+    c.b = w + W_B * h->npad; c.x0 = w + W_X0 * h->npad; c.x_out = w + W_XOUT * h->npad;
+    c.hook_in = w + W_HIN * h->npad; c.hook_out = w + W_HOUT * h->npad;
+    for (int i = 0; i < kNumVec; ++i) c.vec[i] = w + (W_VEC0 + i) * h->npad;
+    c.T.n = (int)h->n;
+    c.T.lo = h->lo.as<double>(); c.T.hi = h->hi.as<double>(); c.T.ekind = h->ekind.as<uint8_t>();
+    c.T.nblk = h->nblk; c.T.bkind = h->bkind.as<int>(); c.T.boff = h->boff.as<int>();
+    c.T.bdim = h->bdim.as<int>(); c.T.bpar = h->bpar.as<double>();
+    c.T.nsmall = h->nsmall; c.T.small_ids = h->small_ids.as<int>();
+    c.T.nbig = h->nbig; c.T.big_ids = h->big_ids.as<int>();
+    c.T.has_cone_ref = h->has_cone_ref;
+    c.T.all_elementwise = (h->nsmall + h->nbig) == 0;
+    c.T.e0 = (int)h->row0; c.T.e1 = (int)(h->row0 + h->nrows);
+    c.partials = h->partials.as<double>();
+    c.andparts = h->andparts.as<unsigned long long>();
+    c.bar_counter = h->flags.as<unsigned>();
+    c.abort_flag = h->flags.as<unsigned>() + 8;
+    c.out = h->out_dev.as<DenseOut>();
+    c.CW = t.CW; c.SW = t.SW; c.np = t.np; c.nseg = t.nseg; c.rows_max = t.rows_max;
+    c.evict_first = ((double)h->nrows * (double)h->n * 8.0 > 96.0 * 1024 * 1024) ? 1 : 0;
+}
+
+template <int OP>
+ccqp_status launch_dense(ccqp_handle* h, DenseCtx& c, const Tiling& t, bool cooperative) {
+    static size_t configured = 0;
+    if (t.smem > configured) {
+        CU(h, cudaFuncSetAttribute(dense_kernel<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
+        configured = 220 * 1024;
+    }
+    CU(h, cudaMemsetAsync(h->flags.p, 0, 64, h->stream));
+    void* args[] = {&c};
+    if (cooperative)
+        CU(h, cudaLaunchCooperativeKernel((const void*)dense_kernel<OP>, dim3(t.grid), dim3(kDenseThreads), args, t.smem, h->stream));
+    else
+        CU(h, cudaLaunchKernel((const void*)dense_kernel<OP>, dim3(t.grid), dim3(kDenseThreads), args, t.smem, h->stream));
+    h->launches += 1;
+    return CCQP_OK;
+}
+
+ccqp_status launch_by_solver(ccqp_handle* h, int solver, DenseCtx& c, const Tiling& t) {
+    switch (solver) {
+        case CCQP_SOLVER_PGD: return launch_dense<OP_PGD>(h, c, t, true);
+        case CCQP_SOLVER_APGD: return launch_dense<OP_APGD>(h, c, t, true);
+        case CCQP_SOLVER_APGD_AR: return launch_dense<OP_APGD_AR>(h, c, t, true);
+        case CCQP_SOLVER_BBPGD: return launch_dense<OP_BBPGD>(h, c, t, true);
+        case CCQP_SOLVER_BBPGDF: return launch_dense<OP_BBPGDF>(h, c, t, true);
+        case CCQP_SOLVER_SPG: return launch_dense<OP_SPG>(h, c, t, true);
+        case CCQP_SOLVER_MPRGP: return launch_dense<OP_MPRGP>(h, c, t, true);
+    }
+    return CCQP_ERR_INVALID_ARG;
+}
+
+bool params_ok(const ccqp_params* p, int solver) {
+    if (!p) return false;
+    if (solver == CCQP_SOLVER_SPG && (p->m < 1 || p->m > kMaxWindow)) return false;
+    return true;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ccqp_abi_version(void) { return CCQP_ABI_VERSION; }
+
+const char* ccqp_status_string(int status) {
+    if (status < 0 || status > 10) return "unknown status";
+    return kStatusText[status];
+}
+
+const char* ccqp_last_error(const ccqp_handle* h) { return h ? h->last_error.c_str() : ""; }
+
+ccqp_status ccqp_create(ccqp_handle** out, int device) {
+    if (!out) return CCQP_ERR_INVALID_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return CCQP_ERR_NO_DEVICE;
+    if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) return CCQP_ERR_NO_DEVICE; }
+    if (device >= count) return CCQP_ERR_INVALID_ARG;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return CCQP_ERR_NO_DEVICE;
+    if (prop.major != 10) return CCQP_ERR_NO_DEVICE;   // kernels are built for sm_100a only
+    ccqp_handle* h = new ccqp_handle();
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess) {
+        delete h;
+        return CCQP_ERR_CUDA;
+    }
+    h->own_stream = true;
+    *out = h;
+    return CCQP_OK;
+}
+
+ccqp_status ccqp_destroy(ccqp_handle* h) {
+    if (!h) return CCQP_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    DevBuf* bufs[] = {&h->a_own, &h->lo, &h->hi, &h->ekind, &h->bkind, &h->boff, &h->bdim, &h->bpar, &h->small_ids,
+                      &h->big_ids, &h->work, &h->partials, &h->andparts, &h->flags, &h->out_dev, &h->uniforms,
+                      &h->batched_ws};
+    for (DevBuf* b : bufs) b->release();
+    if (h->out_host) cudaFreeHost(h->out_host);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return CCQP_OK;
+}
+
+ccqp_status ccqp_set_stream(ccqp_handle* h, void* cuda_stream) {
+    if (!h) return CCQP_ERR_INVALID_ARG;
+    if (h->own_stream && h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+    h->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+    h->own_stream = false;
+    return CCQP_OK;
+}
+
+ccqp_status ccqp_get_info(const ccqp_handle* h, int32_t* sm_count, int32_t* dense_grid, int32_t* dense_threads,
+                          int64_t* dense_smem_bytes) {
+    if (!h) return CCQP_ERR_INVALID_ARG;
+    if (sm_count) *sm_count = h->sm_count;
+    if (dense_threads) *dense_threads = kDenseThreads;
+    if (h->dA) {
+        Tiling t = choose_tiling(h);
+        if (dense_grid) *dense_grid = t.grid;
+        if (dense_smem_bytes) *dense_smem_bytes = (int64_t)t.smem;
+    } else {
+        if (dense_grid) *dense_grid = h->sm_count;
+        if (dense_smem_bytes) *dense_smem_bytes = 0;
+    }
+    return CCQP_OK;
+}
+
+ccqp_status ccqp_set_matrix(ccqp_handle* h, const double* A, int64_t n, int64_t lda, int64_t row_begin, int64_t n_rows,
+                            int memtype) {
+    if (!h || !A || n <= 0 || n >= (1LL << 31) - 256 || lda < n || row_begin < 0 || n_rows <= 0 || row_begin + n_rows > n)
+        return CCQP_ERR_INVALID_ARG;
+    CU(h, cudaSetDevice(h->device));
+    h->n = n; h->row0 = row_begin; h->nrows = n_rows;
+    if (memtype == CCQP_MEM_DEVICE) {
+        h->dA = A; h->lda = lda;
+    } else {
+        const long long ldd = round_up(n, 4);   // keep rows 32-byte aligned for the 256-bit loads
+        CU(h, h->a_own.ensure((size_t)n_rows * ldd * 8 + 64));
+        CU(h, cudaMemcpy2DAsync(h->a_own.p, (size_t)ldd * 8, A, (size_t)lda * 8, (size_t)n * 8, (size_t)n_rows,
+                                cudaMemcpyHostToDevice, h->stream));
+        h->dA = h->a_own.as<double>(); h->lda = ldd;
+    }
+    return CCQP_OK;
+}
+
+ccqp_status ccqp_set_projection(ccqp_handle* h, const ccqp_block* blocks, int64_t n_blocks, const double* params,
+                                int64_t n_params) {
+    if (!h || !blocks || n_blocks <= 0 || (n_params > 0 && !params)) return CCQP_ERR_INVALID_ARG;
+    CU(h, cudaSetDevice(h->device));
+    long long n = 0;
+    for (int64_t k = 0; k < n_blocks; ++k) {
+        const ccqp_block& b = blocks[k];
+        if (b.offset != n || b.dim <= 0 || b.kind < 0 || b.kind > CCQP_BLOCK_SOC || b.param_off < 0) return CCQP_ERR_INVALID_ARG;
+        const long long need = (b.kind == CCQP_BLOCK_IDENTITY) ? 0 : (b.kind == CCQP_BLOCK_BOX) ? 2 * b.dim
+                               : (b.kind == CCQP_BLOCK_LOWER || b.kind == CCQP_BLOCK_UPPER) ? b.dim : 1;
+        if (b.param_off + need > n_params) return CCQP_ERR_INVALID_ARG;
+        n += b.dim;
+    }
+    if (n >= (1LL << 31) - 256) return CCQP_ERR_INVALID_ARG;
+    const long long npad = round_up(n, 64) + 64;
+    const double inf = std::numeric_limits<double>::infinity();
+    std::vector<double> lo(npad, -inf), hi(npad, inf), bpar(n_blocks, 0.0);
+    std::vector<uint8_t> ek(npad, (uint8_t)kIdentity);
+    std::vector<int> bkind(n_blocks), boff(n_blocks), bdim(n_blocks), small_ids, big_ids;
+    int has_cone = 0;
+    for (int64_t k = 0; k < n_blocks; ++k) {
+        const ccqp_block& b = blocks[k];
+        bkind[k] = b.kind; boff[k] = (int)b.offset; bdim[k] = (int)b.dim;
+        const double* p = params ? params + b.param_off : nullptr;
+        switch (b.kind) {
+            case CCQP_BLOCK_IDENTITY: break;
+            case CCQP_BLOCK_LOWER:
+                for (long long j = 0; j < b.dim; ++j) { lo[b.offset + j] = p[j]; ek[b.offset + j] = kLower; }
+                break;
+            case CCQP_BLOCK_UPPER:
+                for (long long j = 0; j < b.dim; ++j) { hi[b.offset + j] = p[j]; ek[b.offset + j] = kUpper; }
+                break;
+            case CCQP_BLOCK_BOX:
+                for (long long j = 0; j < b.dim; ++j) { lo[b.offset + j] = p[j]; hi[b.offset + j] = p[b.dim + j]; ek[b.offset + j] = kBox; }
+                break;
+            default:
+                bpar[k] = p[0];
+                for (long long j = 0; j < b.dim; ++j) ek[b.offset + j] = kElemNorm;
+                (b.dim <= kSmallDim ? small_ids : big_ids).push_back((int)k);
+                if (b.kind == CCQP_BLOCK_CONE_REF) has_cone = 1;
+        }
+    }
+    auto up = [&](DevBuf& d, const void* src, size_t bytes) -> cudaError_t {
+        cudaError_t e = d.ensure(bytes ? bytes : 8);
+        if (e != cudaSuccess || !bytes) return e;
+        return cudaMemcpyAsync(d.p, src, bytes, cudaMemcpyHostToDevice, h->stream);
+    };
+    CU(h, up(h->lo, lo.data(), npad * 8));
+    CU(h, up(h->hi, hi.data(), npad * 8));
+    CU(h, up(h->ekind, ek.data(), npad));
+    CU(h, up(h->bkind, bkind.data(), n_blocks * 4));
+    CU(h, up(h->boff, boff.data(), n_blocks * 4));
+    CU(h, up(h->bdim, bdim.data(), n_blocks * 4));
+    CU(h, up(h->bpar, bpar.data(), n_blocks * 8));
+    CU(h, up(h->small_ids, small_ids.data(), small_ids.size() * 4));
+    CU(h, up(h->big_ids, big_ids.data(), big_ids.size() * 4));
+    CU(h, cudaStreamSynchronize(h->stream));   // the host vectors die here
+    h->nblk = (int)n_blocks; h->nsmall = (int)small_ids.size(); h->nbig = (int)big_ids.size();
+    h->has_cone_ref = has_cone; h->proj_n = n; h->have_proj = true;
+    return CCQP_OK;
+}
+
+ccqp_status ccqp_solve(ccqp_handle* h, int solver, const ccqp_params* params, const double* b, const double* x0,
+                       const double* uniforms, int64_t n_uniforms, double* x_out, int memtype, ccqp_result* result) {
+    if (!h || !b || !x_out || !result || !params_ok(params, solver) || solver < 0 || solver > CCQP_SOLVER_MPRGP)
+        return CCQP_ERR_INVALID_ARG;
+    if (!h->dA || !h->have_proj) return CCQP_ERR_NOT_READY;
+    if (h->proj_n != h->n) return CCQP_ERR_INVALID_ARG;
+    if (h->row0 != 0 || h->nrows != h->n) return CCQP_ERR_UNSUPPORTED;   // sharded solves need ccqp_comm_attach
+    CU(h, cudaSetDevice(h->device));
+    ccqp_status st = ensure_work(h);
+    if (st != CCQP_OK) return st;
+    const long long n = h->n, npad = h->npad;
+    double* w = h->work.as<double>();
+    // zero b/x0 slots (tails must be zero), then fill
+    CU(h, cudaMemsetAsync(w, 0, (size_t)W_COUNT * npad * 8, h->stream));
+    if ((st = copy_in(h, w + W_B * npad, b, n, memtype)) != CCQP_OK) return st;
+    if (x0 && (st = copy_in(h, w + W_X0 * npad, x0, n, memtype)) != CCQP_OK) return st;
+    const Tiling t = choose_tiling(h);
+    DenseCtx c;
+    fill_ctx(h, c, t);
+    c.tol = params->tol; c.max_mv = params->max_mv; c.step = params->step_size;
+    c.tau = params->tau; c.sig1 = params->sigma1; c.sig2 = params->sigma2; c.m = params->m;
+    if (solver == CCQP_SOLVER_SPG) {
+        if (n_uniforms < 0 || (n_uniforms > 0 && !uniforms)) return CCQP_ERR_INVALID_ARG;
+        if (memtype == CCQP_MEM_DEVICE) c.uniforms = uniforms;
+        else {
+            CU(h, h->uniforms.ensure((size_t)std::max<int64_t>(n_uniforms, 1) * 8));
+            if (n_uniforms) CU(h, cudaMemcpyAsync(h->uniforms.p, uniforms, (size_t)n_uniforms * 8, cudaMemcpyHostToDevice, h->stream));
+            c.uniforms = h->uniforms.as<double>();
+        }
+        c.n_uniforms = n_uniforms;
+    }
+    const long long launches0 = h->launches;
+    CU(h, cudaEventRecord(h->ev0, h->stream));
+    if ((st = launch_by_solver(h, solver, c, t)) != CCQP_OK) return st;
+    CU(h, cudaEventRecord(h->ev1, h->stream));
+    CU(h, cudaMemcpyAsync(h->out_host, h->out_dev.p, sizeof(DenseOut), cudaMemcpyDeviceToHost, h->stream));
+    if ((st = copy_out(h, x_out, c.x_out, n, memtype)) != CCQP_OK) return st;
+    cudaError_t e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) {
+        h->last_error = std::string("solver kernel: ") + cudaGetErrorString(e);
+        return e == cudaErrorLaunchFailure ? CCQP_ERR_DEVICE_TIMEOUT : CCQP_ERR_CUDA;
+    }
+    float ms = 0.f;
+    CU(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    const DenseOut* o = reinterpret_cast<const DenseOut*>(h->out_host);
+    std::memset(result, 0, sizeof(*result));
+    result->residual = o->residual;
+    result->gpu_seconds = ms * 1e-3;
+    result->mv_count = o->mv;
+    result->gemv_count = o->gemv;
+    result->iterations = o->iters;
+    result->uniforms_used = o->draws;
+    result->converged = o->converged;
+    result->status = o->status;
+    result->hbm_bytes = (double)o->gemv * (8.0 * (double)h->nrows * (double)n + 8.0 * (double)n + 8.0 * (double)h->nrows);
+    result->kernel_launches = h->launches - launches0;
+    return (ccqp_status)o->status;
+}
+
+static ccqp_status run_hook(ccqp_handle* h, int op, const double* in, double* out, long long n_in, long long n_out,
+                            int memtype) {
+    if (!h || !in || !out) return CCQP_ERR_INVALID_ARG;
+    CU(h, cudaSetDevice(h->device));
+    if (op == OP_GEMV) { if (!h->dA) return CCQP_ERR_NOT_READY; }
+    else {
+        if (!h->have_proj) return CCQP_ERR_NOT_READY;
+        if (!h->dA) { h->n = h->proj_n; h->row0 = 0; h->nrows = h->proj_n; }   // projection-only use
+        else if (h->proj_n != h->n) return CCQP_ERR_INVALID_ARG;
+    }
+    ccqp_status st = ensure_work(h);
+    if (st != CCQP_OK) return st;
+    const long long npad = h->npad;
+    double* w = h->work.as<double>();
+    CU(h, cudaMemsetAsync(w + W_HIN * npad, 0, (size_t)2 * npad * 8, h->stream));
+    if ((st = copy_in(h, w + W_HIN * npad, in, n_in, memtype)) != CCQP_OK) return st;
+    Tiling t;
+    if (h->dA) t = choose_tiling(h);
+    else { t.grid = (int)std::max<long long>(1, std::min<long long>(h->sm_count, h->n)); t.CW = 128; t.SW = 128; t.np = 1; t.nseg = 1; t.rows_max = 1; t.smem = dense_smem_bytes(128, 1, 1); }
+    DenseCtx c;
+    fill_ctx(h, c, t);
+    if (op == OP_GEMV) st = launch_dense<OP_GEMV>(h, c, t, false);
+    else if (op == OP_PROJECT) st = launch_dense<OP_PROJECT>(h, c, t, false);
+    else st = launch_dense<OP_NORMAL>(h, c, t, false);
+    if (st != CCQP_OK) return st;
+    if ((st = copy_out(h, out, c.hook_out, n_out, memtype)) != CCQP_OK) return st;
+    CU(h, cudaStreamSynchronize(h->stream));
+    return CCQP_OK;
+}
+
+ccqp_status ccqp_gemv(ccqp_handle* h, const double* v, double* y, int memtype) {
+    if (!h) return CCQP_ERR_INVALID_ARG;
+    return run_hook(h, OP_GEMV, v, y, h->n, h->nrows, memtype);
+}
+ccqp_status ccqp_project(ccqp_handle* h, const double* x, double* out, int memtype) {
+    if (!h) return CCQP_ERR_INVALID_ARG;
+    return run_hook(h, OP_PROJECT, x, out, h->proj_n, h->proj_n, memtype);
+}
+ccqp_status ccqp_normal(ccqp_handle* h, const double* x, double* out, int memtype) {
+    if (!h) return CCQP_ERR_INVALID_ARG;
+    if (h->has_cone_ref) return CCQP_ERR_NORMAL_NOT_IMPLEMENTED;
+    return run_hook(h, OP_NORMAL, x, out, h->proj_n, h->proj_n, memtype);
+}
+
+ccqp_status ccqp_solve_batched(ccqp_handle* h, int solver, const ccqp_params* params, int64_t batch, int64_t n,
+                               const double* A, const double* b, const double* x0, const double* lb, const double* ub,
+                               const double* uniforms, int64_t n_uniforms, double* x_out, int memtype,
+                               ccqp_result* results, ccqp_result* summary) {
+    if (!h || !params_ok(params, solver) || batch <= 0 || n <= 0 || !A || !b || !lb || !ub || !x_out)
+        return CCQP_ERR_INVALID_ARG;
+    CU(h, cudaSetDevice(h->device));
+    std::string err;
+    int launches = 0;
+    ccqp_status st = (ccqp_status)batched_solve(h->stream, h->sm_count, h->batched_ws.p, h->batched_ws.cap, solver, *params,
+                                                batch, n, A, b, x0, lb, ub, uniforms, n_uniforms, x_out, memtype, results,
+                                                summary, h->ev0, h->ev1, &launches, err,
+                                                [&](size_t bytes) -> void* { return h->batched_ws.ensure(bytes) == cudaSuccess ? h->batched_ws.p : nullptr; });
+    h->launches += launches;
+    if (st == CCQP_ERR_CUDA) h->last_error = err;
+    return st;
+}
+
+ccqp_status ccqp_comm_export(ccqp_handle*, int, int, int64_t, void*) { return CCQP_ERR_UNSUPPORTED; }
+ccqp_status ccqp_comm_attach(ccqp_handle*, const void*) { return CCQP_ERR_UNSUPPORTED; }
+ccqp_status ccqp_comm_detach(ccqp_handle*) { return CCQP_ERR_UNSUPPORTED; }
+
+}  // extern "C"

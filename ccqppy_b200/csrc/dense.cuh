@@ -1,0 +1,807 @@
+// Dense CCQP solvers as ONE persistent cooperative kernel per solve (sm_100a).
+//
+// Layout of a solve on the device
+//   * grid = one CTA per SM (kDenseThreads threads), launched cooperatively; CTA c owns a
+//     contiguous band of rows of the (row-shard of the) Hessian A for every mat-vec of the solve.
+//   * the solver loop of the reference (solvers.py) runs entirely inside the kernel: phases are
+//     separated by a grid barrier; scalar control flow (step lengths, stopping tests, branch
+//     choices) is evaluated redundantly and bit-identically by every thread from
+//     deterministically reduced partial sums, so all CTAs take the same branches with no host
+//     round trip.
+//   * mat-vec phase (gemv_phase): the input vector is staged into shared memory in column panels
+//     by the TMA engine (cp.async.bulk + mbarrier, double buffered); A is streamed exactly once
+//     with 256-bit read-only loads (8 in flight per lane), FMA-accumulated per lane and reduced
+//     with warp shuffles; work inside a CTA is split into (row, column-segment) tasks so that all
+//     warps stay busy even when a CTA owns only a few rows (the 8-GPU row shard).  The epilogue
+//     functor of each solver fuses "+ b", the vector updates and the row-local dot products.
+//   * elementwise phases (projection, axpy, residual terms, masks) run over the grid with the
+//     functor-based project_pass of proj.cuh.
+//
+// Algorithmic bytes per mat-vec: 8 * n_rows * n (A) + 8 n (v) + 8 n_rows (y)   (SURVEY 8d).
+#pragma once
+#include "proj.cuh"
+
+namespace ccqp {
+
+constexpr int kDenseThreads = 512;
+constexpr int kDenseWarps = kDenseThreads / 32;
+constexpr int kUnroll = 8;            // 256-bit loads in flight per lane
+constexpr int kMaxRed = 8;            // doubles per grid reduction
+constexpr int kMaxWindow = 64;        // SPG non-monotone window
+
+enum DenseOp : int {
+    OP_PGD = 0, OP_APGD = 1, OP_APGD_AR = 2, OP_BBPGD = 3, OP_BBPGDF = 4, OP_SPG = 5, OP_MPRGP = 6,
+    OP_GEMV = 100, OP_PROJECT = 101, OP_NORMAL = 102
+};
+
+struct DenseOut {          // written by CTA 0 / thread 0
+    double residual;
+    long long mv, gemv, iters, draws;
+    int converged, status;
+};
+
+constexpr int kNumVec = 12;
+
+struct DenseCtx {
+    // Hessian row shard
+    const double* A;
+    long long lda;
+    int n;              // columns = unknowns
+    int row0, nrows;    // rows [row0, row0+nrows) live on this device
+    int aligned;        // 256-bit path usable (A base and lda*8 multiples of 32 bytes)
+    const double* b;    // [npad]
+    const double* x0;   // [npad] (zeros if the caller passed none)
+    ProjTable T;
+    double* vec[kNumVec];   // work vectors, [npad] each, zero tails
+    double* partials;       // [2][grid][kMaxRed]
+    unsigned long long* andparts;   // [2][grid]
+    unsigned* bar_counter;
+    unsigned* abort_flag;
+    const double* uniforms;
+    long long n_uniforms;
+    double tol, max_mv, step, tau, sig1, sig2;
+    int m;
+    double* x_out;      // [npad]
+    DenseOut* out;
+    // mat-vec tiling
+    int CW;             // panel width (columns staged in shared memory at a time), multiple of 128
+    int SW;             // task segment width, multiple of 128, divides CW
+    int np;             // number of panels
+    int nseg;           // total segments per row
+    int rows_max;       // max rows owned by one CTA
+    int evict_first;    // stream A with L2 evict-first
+    // test hooks
+    const double* hook_in;
+    double* hook_out;
+};
+
+// shared memory carve-up (dynamic)
+struct DenseSmem {
+    double* vbuf[2];
+    double* psum;
+    double* scratch;        // kMaxRed*32 doubles
+    uint64_t* mbar;         // 2
+    unsigned long long* ascratch;   // 32
+};
+
+__host__ __device__ inline size_t dense_smem_bytes(int CW, int rows_max, int nseg) {
+    size_t s = 0;
+    s += 2 * (size_t)CW * 8;
+    s += (size_t)rows_max * nseg * 8;
+    s += kMaxRed * 32 * 8;
+    s += 32 * 8;
+    s += 2 * 8;
+    return s + 128;
+}
+
+struct Kst {                // per-thread kernel state
+    GridSync gs;
+    DenseSmem sm;
+    int gtid, gstride;
+    int r0, r1;             // rows of this CTA (global indices)
+    unsigned par[2];        // mbarrier phase parity per buffer
+    int redbuf;             // partial-buffer parity
+    long long mv, gemv, iters, draws;
+};
+
+// ------------------------------------------------------------------------------------------
+// reductions across the grid (the barrier also orders all prior global writes)
+// ------------------------------------------------------------------------------------------
+template <int K>
+__device__ __forceinline__ void reduce_sync(Kst& k, const DenseCtx& c, double (&a)[K]) {
+    static_assert(K <= kMaxRed, "too many reduction slots");
+    cta_sum<K>(a, k.sm.scratch);
+    const int G = gridDim.x;
+    double* part = c.partials + (size_t)k.redbuf * G * kMaxRed;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int j = 0; j < K; ++j) part[(size_t)blockIdx.x * kMaxRed + j] = a[j];
+    }
+    grid_barrier(k.gs);
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            double s = 0.0;
+            for (int q = lane; q < G; q += 32) s += ld_cg(part + (size_t)q * kMaxRed + j);
+            s = warp_sum(s);
+            if (lane == 0) k.sm.scratch[j] = s;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < K; ++j) a[j] = k.sm.scratch[j];
+    __syncthreads();
+    k.redbuf ^= 1;
+}
+
+__device__ __forceinline__ void barrier_only(Kst& k) { grid_barrier(k.gs); }
+
+// bitwise AND of a 64-bit mask over the grid
+__device__ __forceinline__ unsigned long long and_sync(Kst& k, const DenseCtx& c, unsigned long long m) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    m = warp_and64(m);
+    if (lane == 0) k.sm.ascratch[warp] = m;
+    __syncthreads();
+    const int G = gridDim.x;
+    unsigned long long* part = c.andparts + (size_t)k.redbuf * G;
+    if (threadIdx.x == 0) {
+        unsigned long long t = ~0ull;
+        for (int w = 0; w < kDenseWarps; ++w) t &= k.sm.ascratch[w];
+        part[blockIdx.x] = t;
+    }
+    grid_barrier(k.gs);
+    if (threadIdx.x < 32) {
+        unsigned long long t = ~0ull;
+        for (int q = lane; q < G; q += 32) {
+            unsigned long long v;
+            asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(v) : "l"(part + q) : "memory");
+            t &= v;
+        }
+        t = warp_and64(t);
+        if (lane == 0) k.sm.ascratch[0] = t;
+    }
+    __syncthreads();
+    const unsigned long long r = k.sm.ascratch[0];
+    __syncthreads();
+    k.redbuf ^= 1;
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------
+// mat-vec phase
+// ------------------------------------------------------------------------------------------
+template <bool kEF>
+__device__ __forceinline__ double dot_seg_aligned(const double* __restrict__ arow, const double* vs, int ncol,
+                                                  int lane) {
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    const int nchunk = ncol >> 7;
+    const double* ap = arow + lane * 4;
+    const double* vp = vs + lane * 4;
+    int c = 0;
+    for (; c + kUnroll <= nchunk; c += kUnroll) {
+        double r[kUnroll][4];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) ldg256_stream<kEF>(ap + (size_t)(c + u) * 128, r[u]);
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const double4 v = *reinterpret_cast<const double4*>(vp + (size_t)(c + u) * 128);
+            a0 = fma(r[u][0], v.x, a0);
+            a1 = fma(r[u][1], v.y, a1);
+            a2 = fma(r[u][2], v.z, a2);
+            a3 = fma(r[u][3], v.w, a3);
+        }
+    }
+    for (; c < nchunk; ++c) {
+        double r[4];
+        ldg256_stream<kEF>(ap + (size_t)c * 128, r);
+        const double4 v = *reinterpret_cast<const double4*>(vp + (size_t)c * 128);
+        a0 = fma(r[0], v.x, a0);
+        a1 = fma(r[1], v.y, a1);
+        a2 = fma(r[2], v.z, a2);
+        a3 = fma(r[3], v.w, a3);
+    }
+    const int col = (nchunk << 7) + lane * 4;
+    if (col < ncol) {
+        a0 = fma(ldg_stream(arow + col), vs[col], a0);
+        if (col + 1 < ncol) a1 = fma(ldg_stream(arow + col + 1), vs[col + 1], a1);
+        if (col + 2 < ncol) a2 = fma(ldg_stream(arow + col + 2), vs[col + 2], a2);
+        if (col + 3 < ncol) a3 = fma(ldg_stream(arow + col + 3), vs[col + 3], a3);
+    }
+    return (a0 + a1) + (a2 + a3);
+}
+
+// any alignment / any lda: 64-bit loads, lanes contiguous
+__device__ __forceinline__ double dot_seg_generic(const double* __restrict__ arow, const double* vs, int ncol,
+                                                  int lane) {
+    double a0 = 0.0, a1 = 0.0;
+    int c = lane;
+    for (; c + 32 < ncol; c += 64) {
+        const double x0 = ldg_stream(arow + c), x1 = ldg_stream(arow + c + 32);
+        a0 = fma(x0, vs[c], a0);
+        a1 = fma(x1, vs[c + 32], a1);
+    }
+    if (c < ncol) a0 = fma(ldg_stream(arow + c), vs[c], a0);
+    return a0 + a1;
+}
+
+// y_row = sum_j A[row][j] v[j] for the rows of this CTA; epi(row, y_row) is called once per row.
+// v: full-length global vector (npad entries, zero tail), complete before the phase starts.
+template <class Epi>
+__device__ __forceinline__ void gemv_phase(Kst& k, const DenseCtx& c, const double* v, Epi epi) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = c.n, CW = c.CW, SW = c.SW, np = c.np, nseg = c.nseg;
+    const int nrows_cta = k.r1 - k.r0;
+    const int spp_full = CW / SW;
+
+    auto panel_cols = [&](int p) { return min(CW, n - p * CW); };
+    auto issue = [&](int p, int buf) {
+        const uint32_t bytes = (uint32_t)(((panel_cols(p) + 1) & ~1) * 8);
+        mbar_expect_tx(&k.sm.mbar[buf], bytes);
+        bulk_g2s(k.sm.vbuf[buf], v + (size_t)p * CW, bytes, &k.sm.mbar[buf]);
+    };
+    if (tid == 0) {
+        fence_proxy_async();
+        issue(0, 0);
+        if (np > 1) issue(1, 1);
+    }
+    for (int p = 0; p < np; ++p) {
+        const int buf = p & 1;
+        mbar_wait(&k.sm.mbar[buf], k.par[buf]);
+        k.par[buf] ^= 1u;
+        const int pc = panel_cols(p);
+        const int spp = (pc + SW - 1) / SW;
+        const int ntask = nrows_cta * spp;
+        const double* vb = k.sm.vbuf[buf];
+        for (int t = warp; t < ntask; t += kDenseWarps) {
+            const int row = t / spp, seg = t - row * spp;
+            const int col0 = seg * SW;
+            const int ncol = min(SW, pc - col0);
+            const double* arow = c.A + (size_t)(k.r0 - c.row0 + row) * c.lda + (size_t)p * CW + col0;
+            double acc;
+            if (c.aligned) acc = c.evict_first ? dot_seg_aligned<true>(arow, vb + col0, ncol, lane)
+                                               : dot_seg_aligned<false>(arow, vb + col0, ncol, lane);
+            else acc = dot_seg_generic(arow, vb + col0, ncol, lane);
+            acc = warp_sum(acc);
+            if (lane == 0) k.sm.psum[(size_t)row * nseg + p * spp_full + seg] = acc;
+        }
+        __syncthreads();   // every warp is done with vbuf[buf]; psum of this panel is visible
+        if (tid == 0 && p + 2 < np) { fence_proxy_async(); issue(p + 2, buf); }
+    }
+    k.gemv += 1;
+    for (int r = tid; r < nrows_cta; r += kDenseThreads) {
+        const double* ps = k.sm.psum + (size_t)r * nseg;
+        double s = ps[0];
+        for (int q = 1; q < nseg; ++q) s += ps[q];
+        epi(k.r0 + r, s);
+    }
+    __syncthreads();       // psum is free again
+}
+
+// ------------------------------------------------------------------------------------------
+// small helpers for the solver programs
+// ------------------------------------------------------------------------------------------
+#define CCQP_ELEMS(i) for (int i = c.T.e0 + k.gtid; i < c.T.e1; i += k.gstride)
+
+__device__ __forceinline__ void swap_ptr(double*& a, double*& b) { double* t = a; a = b; b = t; }
+
+// residual probe of solvers.py:137-139: sum over i of (cs * (x_i - P(x - gd*g)_i))^2
+// (the reference scales the vector first and then takes the 2-norm)
+template <class XF, class GF>
+__device__ __forceinline__ double residual_partial(Kst& k, const DenseCtx& c, double cs, XF xf, GF gf) {
+    double acc = 0.0;
+    project_pass(c.T, k.gtid, k.gstride, k.sm.scratch,
+                 [&](int i) { return xf(i) - kGd * gf(i); },
+                 [&](int i, double, double p) { const double d = cs * (xf(i) - p); acc = fma(d, d, acc); });
+    return acc;
+}
+
+__device__ __forceinline__ void finish(Kst& k, const DenseCtx& c, const double* xsol, double res, int status) {
+    CCQP_ELEMS(i) c.x_out[i] = ld_cg(xsol + i);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        DenseOut o;
+        o.residual = res;
+        o.mv = k.mv; o.gemv = k.gemv; o.iters = k.iters; o.draws = k.draws;
+        o.converged = ((double)k.mv < c.max_mv) ? 1 : 0;
+        o.status = status;
+        *c.out = o;
+    }
+}
+
+__device__ __forceinline__ bool hit_max(const Kst& k, const DenseCtx& c) { return (double)k.mv >= c.max_mv; }
+
+// ------------------------------------------------------------------------------------------
+// PGD / BBPGD / BBPGDf                          solvers.py:114-170, 606-669, 741-819
+// ------------------------------------------------------------------------------------------
+template <int MODE>
+__device__ void solve_pgd_family(Kst& k, const DenseCtx& c) {
+    double *x = c.vec[0], *xm = c.vec[1], *g = c.vec[2], *gm = c.vec[3];
+    double *xmin = c.vec[4], *gmin = c.vec[5];
+    const double cs = 1.0 / (3 * (double)c.n * kGd);
+    const double* b = c.b;
+    CCQP_ELEMS(i) { const double v = c.x0[i]; x[i] = v; xm[i] = v; if (MODE == OP_BBPGDF) { xmin[i] = v; gmin[i] = v; } }
+    barrier_only(k);
+    gemv_phase(k, c, xm, [&](int r, double s) { gm[r] = s + b[r]; });
+    k.mv = 1;
+    barrier_only(k);
+    double a1[1] = {residual_partial(k, c, cs, [&](int i) { return ld_cg(xm + i); }, [&](int i) { return ld_cg(gm + i); })};
+    reduce_sync<1>(k, c, a1);
+    double res = sqrt(a1[0]);
+    double resmin = INFINITY;
+    const double* xsol = x;
+    if (res >= c.tol) {
+        double step = c.step;
+        if (MODE != OP_PGD) {   // alpha0 = g.g / g.Ag, product not counted (:635, :775)
+            double a2[2] = {0.0, 0.0};
+            gemv_phase(k, c, gm, [&](int r, double s) { const double gr = ld_cg(gm + r); a2[0] = fma(gr, s, a2[0]); a2[1] = fma(gr, gr, a2[1]); });
+            reduce_sync<2>(k, c, a2);
+            step = a2[1] / a2[0];
+        }
+        for (;;) {
+            project_pass(c.T, k.gtid, k.gstride, k.sm.scratch,
+                         [&](int i) { return ld_cg(xm + i) - step * ld_cg(gm + i); },
+                         [&](int i, double, double p) { x[i] = p; });
+            barrier_only(k);
+            gemv_phase(k, c, x, [&](int r, double s) { g[r] = s + b[r]; });
+            k.mv += 1;
+            barrier_only(k);
+            xsol = x;
+            if (hit_max(k, c)) break;
+            double a3[3] = {0.0, 0.0, 0.0};
+            project_pass(c.T, k.gtid, k.gstride, k.sm.scratch,
+                         [&](int i) { return ld_cg(x + i) - kGd * ld_cg(g + i); },
+                         [&](int i, double, double p) {
+                             const double xi = ld_cg(x + i);
+                             const double d = cs * (xi - p);
+                             a3[0] = fma(d, d, a3[0]);
+                             if (MODE != OP_PGD) {
+                                 const double s = xi - ld_cg(xm + i), y = ld_cg(g + i) - ld_cg(gm + i);
+                                 a3[1] = fma(s, s, a3[1]);
+                                 a3[2] = fma(s, y, a3[2]);
+                             }
+                         });
+            reduce_sync<3>(k, c, a3);
+            res = sqrt(a3[0]);
+            k.iters += 1;
+            if (res < c.tol) break;
+            if (MODE == OP_BBPGDF) {   // :793-800
+                if (res < resmin) {
+                    resmin = res;
+                    CCQP_ELEMS(i) { xmin[i] = ld_cg(x + i); gmin[i] = ld_cg(g + i); }
+                }
+                if (step < 10 * kEps) {   // stagnation: x replaced (g is not), BB sums redone
+                    barrier_only(k);
+                    project_pass(c.T, k.gtid, k.gstride, k.sm.scratch,
+                                 [&](int i) { return ld_cg(xmin + i) - kGd * ld_cg(gmin + i); },
+                                 [&](int i, double, double p) { x[i] = p; });
+                    barrier_only(k);
+                    double a2[2] = {0.0, 0.0};
+                    CCQP_ELEMS(i) {
+                        const double s = ld_cg(x + i) - ld_cg(xm + i), y = ld_cg(g + i) - ld_cg(gm + i);
+                        a2[0] = fma(s, s, a2[0]);
+                        a2[1] = fma(s, y, a2[1]);
+                    }
+                    reduce_sync<2>(k, c, a2);
+                    a3[1] = a2[0]; a3[2] = a2[1];
+                }
+            }
+            if (MODE != OP_PGD) step = a3[1] / (a3[2] + 10 * kEps);
+            swap_ptr(x, xm);
+            swap_ptr(g, gm);
+        }
+    }
+    barrier_only(k);
+    finish(k, c, xsol, res, 0);
+}
+
+// ------------------------------------------------------------------------------------------
+// SPG-QP                                                           solvers.py:906-975
+// ------------------------------------------------------------------------------------------
+__device__ void solve_spg(Kst& k, const DenseCtx& c) {
+    double *x = c.vec[0], *g = c.vec[1], *d = c.vec[2], *Ad = c.vec[3];
+    const double* b = c.b;
+    CCQP_ELEMS(i) x[i] = c.x0[i];
+    barrier_only(k);
+    double a2[2] = {0.0, 0.0};
+    gemv_phase(k, c, x, [&](int r, double s) {
+        const double gr = s + b[r];
+        g[r] = gr;
+        a2[0] = fma(gr, ld_cg(x + r), a2[0]);   // f0 = g.x (:923, kept as written)
+        a2[1] = fma(gr, gr, a2[1]);
+    });
+    reduce_sync<2>(k, c, a2);
+    double f = a2[0];
+    const double gg = a2[1];
+    double a1[1] = {0.0};
+    gemv_phase(k, c, g, [&](int r, double s) { a1[0] = fma(ld_cg(g + r), s, a1[0]); });
+    reduce_sync<1>(k, c, a1);
+    double alpha = gg / a1[0];
+    k.mv = 2;
+    double window[kMaxWindow];
+    int wcount = 1, whead = 0;          // ring buffer = deque(maxlen=m)
+    window[0] = f;
+    double dd_rep = NAN;                 // residual reported = sqrt(d.d) of the last completed test
+    double bk = 0.0;                     // pending update x += bk d, g += bk Ad (applied lazily)
+    int status = 0;
+    for (;;) {
+        double s2[2] = {0.0, 0.0};       // d.d, d.g
+        project_pass(c.T, k.gtid, k.gstride, k.sm.scratch,
+                     [&](int i) {
+                         const double xi = fma(bk, ld_cg(d + i), ld_cg(x + i));
+                         const double gi = fma(bk, ld_cg(Ad + i), ld_cg(g + i));
+                         return xi - alpha * gi;
+                     },
+                     [&](int i, double, double p) {
+                         // x += bk*d ; g += bk*Ad  (:961-962) fused with d = P(x - alpha g) - x (:937)
+                         const double xi = fma(bk, ld_cg(d + i), ld_cg(x + i));
+                         const double gi = fma(bk, ld_cg(Ad + i), ld_cg(g + i));
+                         const double di = p - xi;
+                         x[i] = xi; g[i] = gi; d[i] = di;
+                         s2[0] = fma(di, di, s2[0]);
+                         s2[1] = fma(di, gi, s2[1]);
+                     });
+        bk = 0.0;
+        reduce_sync<2>(k, c, s2);
+        double s1[1] = {0.0};
+        gemv_phase(k, c, d, [&](int r, double s) { Ad[r] = s; s1[0] = fma(ld_cg(d + r), s, s1[0]); });
+        k.mv += 1;
+        reduce_sync<1>(k, c, s1);
+        if (hit_max(k, c)) break;
+        const double dd = s2[0], dg = s2[1], dAd = s1[0];
+        dd_rep = dd;
+        if (sqrt(dd) <= c.tol) break;
+        double fmax = window[0];
+        for (int j = 1; j < wcount; ++j) fmax = fmax > window[j] ? fmax : window[j];
+        const double xi = (fmax - f) / dAd;
+        const double beta = -dg / dAd;
+        const double bhat = c.tau * beta + sqrt((c.tau * c.tau) * (beta * beta) + 2 * xi);
+        // Python's min(bhat, sig2): sig2 only if sig2 < bhat, so a NaN bhat is kept
+        const double hi = (c.sig2 < bhat) ? c.sig2 : bhat;
+        if (hi != hi) { status = 8; break; }                       // CCQP_ERR_RANGE
+        if (k.draws >= c.n_uniforms) { status = 7; break; }        // CCQP_ERR_UNIFORMS_EXHAUSTED
+        const double u = c.uniforms[k.draws];
+        k.draws += 1;
+        bk = c.sig1 + (hi - c.sig1) * u;
+        f += bk * bk * dg + 0.5 * (bk * bk) * dAd;                  // :963 as written
+        if (wcount < c.m) { window[wcount++] = f; }
+        else { window[whead] = f; whead = (whead + 1) % c.m; }
+        alpha = dd / dAd;
+        k.iters += 1;
+    }
+    barrier_only(k);
+    finish(k, c, x, sqrt(dd_rep), status);
+}
+
+// ------------------------------------------------------------------------------------------
+// APGD and its anti-relaxation variant              solvers.py:242-343, 415-533
+// ------------------------------------------------------------------------------------------
+template <bool AR>
+__device__ void solve_apgd(Kst& k, const DenseCtx& c) {
+    double *x = c.vec[0], *xp = c.vec[1], *y = c.vec[2], *yn = c.vec[3], *g = c.vec[4], *Axp = c.vec[5];
+    double *xhat = c.vec[6], *v0 = c.vec[7];
+    const double* b = c.b;
+    const double cs = 1.0 / (3 * (double)c.n * kGd);
+    double a1[1] = {0.0};
+    CCQP_ELEMS(i) {
+        const double v = c.x0[i];
+        x[i] = v; y[i] = v; xp[i] = v;
+        if (AR) xhat[i] = 1.0;
+        const double dv = v - 1.0;
+        v0[i] = dv;
+        a1[0] = fma(dv, dv, a1[0]);
+    }
+    reduce_sync<1>(k, c, a1);
+    const double dn2 = a1[0];
+    a1[0] = 0.0;
+    gemv_phase(k, c, v0, [&](int, double s) { a1[0] = fma(s, s, a1[0]); });
+    reduce_sync<1>(k, c, a1);
+    double L = sqrt(a1[0]) / sqrt(dn2);
+    double t = 1.0 / L;
+    k.mv = 1;
+    double theta = 1.0, res = NAN, resmin = INFINITY;
+    for (;;) {
+        double r12[2] = {0.0, 0.0};
+        gemv_phase(k, c, y, [&](int r, double s) {
+            const double yr = ld_cg(y + r), br = b[r];
+            g[r] = s + br;
+            r12[0] = fma(yr, s, r12[0]);
+            r12[1] = fma(yr, br, r12[1]);
+        });
+        k.mv += 1;
+        reduce_sync<2>(k, c, r12);
+        if (hit_max(k, c)) break;
+        const double rt1 = r12[0] * 0.5, rt2 = r12[1];
+        project_pass(c.T, k.gtid, k.gstride, k.sm.scratch,
+                     [&](int i) { return ld_cg(y + i) - t * ld_cg(g + i); },
+                     [&](int i, double, double p) { xp[i] = p; });
+        barrier_only(k);
+        for (;;) {   // Lipschitz backtracking :288-310
+            double q[4] = {0.0, 0.0, 0.0, 0.0};
+            gemv_phase(k, c, xp, [&](int r, double s) {
+                Axp[r] = s;
+                const double xr = ld_cg(xp + r), df = xr - ld_cg(y + r);
+                q[0] = fma(xr, s, q[0]);
+                q[1] = fma(xr, b[r], q[1]);
+                q[2] = fma(ld_cg(g + r), df, q[2]);
+                q[3] = fma(df, df, q[3]);
+            });
+            k.mv += 1;
+            reduce_sync<4>(k, c, q);
+            if (hit_max(k, c)) break;   // leaves the inner loop only (:292-293)
+            const double lt1 = q[0] * 0.5, lt2 = q[1], rt3 = q[2], rt4 = 0.5 * L * q[3];
+            if ((lt1 + lt2) <= (rt1 + rt2 + rt3 + rt4)) break;
+            L *= 2;
+            t = 1.0 / L;
+            project_pass(c.T, k.gtid, k.gstride, k.sm.scratch,
+                         [&](int i) { return ld_cg(y + i) - t * ld_cg(g + i); },
+                         [&](int i, double, double p) { xp[i] = p; });
+            barrier_only(k);
+        }
+        double theta_n = 0.5 * (-theta * theta + theta * sqrt(4 + theta * theta));
+        const double beta = theta * (1 - theta) / (theta * theta + theta_n);
+        double r2[2] = {0.0, 0.0};
+        project_pass(c.T, k.gtid, k.gstride, k.sm.scratch,
+                     [&](int i) { return ld_cg(xp + i) - kGd * (ld_cg(Axp + i) + b[i]); },
+                     [&](int i, double, double p) {
+                         const double xpi = ld_cg(xp + i), xi = ld_cg(x + i);
+                         const double dr = cs * (xpi - p);
+                         r2[0] = fma(dr, dr, r2[0]);
+                         if (AR) r2[1] = fma(ld_cg(g + i), xpi - xi, r2[1]);
+                         yn[i] = (1 + beta) * xpi - beta * xi;
+                     });
+        reduce_sync<2>(k, c, r2);
+        res = sqrt(r2[0]);
+        k.iters += 1;
+        if (AR && res < resmin) {
+            resmin = res;
+            CCQP_ELEMS(i) xhat[i] = ld_cg(xp + i);
+        }
+        if (res < c.tol) break;
+        if (AR && r2[1] > 0) {   // :510-512
+            CCQP_ELEMS(i) yn[i] = ld_cg(xp + i);
+            theta_n = 1;
+            barrier_only(k);
+        }
+        L *= 0.9;
+        t = 1.0 / L;
+        swap_ptr(y, yn);
+        swap_ptr(x, xp);   // afterwards xp names the previous x (what :336 returns on the mv limit)
+        theta = theta_n;
+    }
+    barrier_only(k);
+    finish(k, c, AR ? xhat : xp, res, 0);
+}
+
+// ------------------------------------------------------------------------------------------
+// MPRGP with BB / expansion steps                                 solvers.py:1048-1200
+// ------------------------------------------------------------------------------------------
+// Feasibility bisection (:1112-1118) in one pass: bit j of the result is set iff
+// all(isclose(yf, P(yf))) holds for yf = x - (af * 2^-j) p.  Halving is exact in fp64, so the
+// step lengths tested are bit-identical to the reference's alpha_f *= 0.5 sequence.
+__device__ unsigned long long bisect_mask(Kst& k, const DenseCtx& c, const double* x, const double* p, double af) {
+    unsigned long long m = ~0ull;
+    const ProjTable& T = c.T;
+    CCQP_ELEMS(i) {
+        const int kd = T.ekind[i];
+        if (kd == kElemNorm || kd == kIdentity) continue;
+        const double xi = ld_cg(x + i), pi = ld_cg(p + i), lo = T.lo[i], hi = T.hi[i];
+        double a = af;
+        for (int j = 0; j < 64; ++j, a *= 0.5) {
+            const double yf = xi - a * pi;
+            if (!is_close(yf, clamp_elem(kd, yf, lo, hi))) m &= ~(1ull << j);
+        }
+    }
+    if (!T.all_elementwise) {
+        double a = af;
+        for (int j = 0; j < 64; ++j, a *= 0.5) {
+            bool ok = true;
+            project_pass<false>(T, k.gtid, k.gstride, k.sm.scratch,
+                                [&](int i) { return ld_cg(x + i) - a * ld_cg(p + i); },
+                                [&](int, double t, double pr) { if (!is_close(t, pr)) ok = false; });
+            if (!ok) m &= ~(1ull << j);
+        }
+    }
+    return and_sync(k, c, m);
+}
+
+__device__ void solve_mprgp(Kst& k, const DenseCtx& c) {
+    double *xk = c.vec[0], *xn = c.vec[1], *gk = c.vec[2], *gn = c.vec[3], *p = c.vec[4], *Ap = c.vec[5];
+    double *nv = c.vec[6], *w = c.vec[7], *dl = c.vec[8];
+    const double* b = c.b;
+    const double cs = 1.0 / (3 * (double)c.n * kGd);
+    int status = 0;
+    project_pass(c.T, k.gtid, k.gstride, k.sm.scratch, [&](int i) { return c.x0[i]; },
+                 [&](int i, double, double pr) { xk[i] = pr; xn[i] = pr; });
+    barrier_only(k);
+    gemv_phase(k, c, xk, [&](int r, double s) { const double v = s + b[r]; gk[r] = v; gn[r] = v; });
+    k.mv = 1;
+    barrier_only(k);
+    double a1[1] = {residual_partial(k, c, cs, [&](int i) { return ld_cg(xk + i); }, [&](int i) { return ld_cg(gk + i); })};
+    reduce_sync<1>(k, c, a1);
+    double res = sqrt(a1[0]);
+    if (res >= c.tol) {
+        double a2[2] = {0.0, 0.0};
+        gemv_phase(k, c, gk, [&](int r, double s) { const double gr = ld_cg(gk + r); a2[0] = fma(gr, s, a2[0]); a2[1] = fma(gr, gr, a2[1]); });
+        k.mv += 1;                                   // counted (:1077-1078)
+        reduce_sync<2>(k, c, a2);
+        double abb = a2[1] / a2[0];
+        bool abb_lazy = false;                       // true: abb = BB(xk - xn) still to be evaluated
+        project_pass(c.T, k.gtid, k.gstride, k.sm.scratch, [&](int i) { return ld_cg(xk + i); },
+                     [&](int i, double t, double pr) { p[i] = is_close(t, pr) ? ld_cg(gk + i) : 0.0; });
+        barrier_only(k);
+        for (;;) {
+            gemv_phase(k, c, xk, [&](int r, double s) { gk[r] = s + b[r]; });
+            k.mv += 1;
+            barrier_only(k);
+            if (hit_max(k, c)) break;
+            // delta = isclose(xk, P(xk)); psi = delta*gk   (:1093-1094)
+            double q3[3] = {0.0, 0.0, 0.0};          // psi.psi, psi.p, #(!delta)
+            project_pass(c.T, k.gtid, k.gstride, k.sm.scratch, [&](int i) { return ld_cg(xk + i); },
+                         [&](int i, double t, double pr) {
+                             const bool cl = is_close(t, pr);
+                             const double psi = cl ? ld_cg(gk + i) : 0.0;
+                             q3[0] = fma(psi, psi, q3[0]);
+                             q3[1] = fma(psi, ld_cg(p + i), q3[1]);
+                             if (!cl) q3[2] += 1.0;
+                             dl[i] = cl ? 1.0 : 0.0;
+                         });
+            reduce_sync<3>(k, c, q3);
+            if (c.T.has_cone_ref) { status = 6; break; }   // normal_vector raises (:1095, ss:465)
+            double betbet = 0.0;
+            if (q3[2] > 0.0) {
+                // rare: some entries of xk are not (close to) feasible; the chopped gradient
+                // needs normal_vector(xk) and the GLOBAL n.g (:1095-1097)
+                normal_pass(c.T, k.gtid, k.gstride, k.sm.scratch, [&](int i) { return ld_cg(xk + i); }, nv);
+                barrier_only(k);
+                double s1[1] = {0.0};
+                CCQP_ELEMS(i) s1[0] = fma(ld_cg(nv + i), ld_cg(gk + i), s1[0]);
+                reduce_sync<1>(k, c, s1);
+                const double mng = s1[0] < 0.0 ? s1[0] : 0.0;    // np.min([0, n.g])
+                double s2[1] = {0.0};
+                CCQP_ELEMS(i) {
+                    const double bv = (1.0 - ld_cg(dl + i)) * (ld_cg(gk + i) - mng * ld_cg(nv + i));
+                    s2[0] = fma(bv, bv, s2[0]);
+                }
+                reduce_sync<1>(k, c, s2);
+                betbet = s2[0];
+            }
+            if (betbet < q3[0]) {
+                double s1[1] = {0.0};
+                gemv_phase(k, c, p, [&](int r, double s) { Ap[r] = s; s1[0] = fma(ld_cg(p + r), s, s1[0]); });
+                k.mv += 1;
+                reduce_sync<1>(k, c, s1);
+                if (hit_max(k, c)) break;
+                const double pAp = s1[0];
+                const double acg = q3[1] / pAp;
+                double af = acg + 10 * kEps;
+                for (int pass = 0;; ++pass) {         // :1112-1118
+                    const unsigned long long m = bisect_mask(k, c, xk, p, af);
+                    if (m) { const int j = __ffsll((long long)m) - 1; for (int q = 0; q < j; ++q) af *= 0.5; break; }
+                    for (int q = 0; q < 64; ++q) af *= 0.5;
+                    if (pass >= 20) break;            // af == 0 by now; the reference would spin forever
+                }
+                if (acg <= af) {
+                    // conjugate-gradient step :1121-1135
+                    project_pass(c.T, k.gtid, k.gstride, k.sm.scratch,
+                                 [&](int i) { return ld_cg(xk + i) - acg * ld_cg(p + i); },
+                                 [&](int i, double yv, double pr) {
+                                     const double api = ld_cg(Ap + i);
+                                     const double gni = ld_cg(gk + i) - acg * api;
+                                     xn[i] = yv;
+                                     gn[i] = gni;
+                                     const double psy = is_close(yv, pr) ? gni : 0.0;
+                                     const double bet = psy * api / pAp;          // elementwise "beta" (:1134)
+                                     p[i] = psy - bet * ld_cg(p + i);
+                                 });
+                    abb_lazy = true;   // same element->thread map as the residual pass: no barrier
+                } else {
+                    // expansion step with a BB step length :1136-1163
+                    double s2[2] = {0.0, 0.0};
+                    CCQP_ELEMS(i) {
+                        const double xi = ld_cg(xk + i), gi = ld_cg(gk + i);
+                        const double xh = xi - af * ld_cg(p + i), gh = gi - af * ld_cg(Ap + i);
+                        const double sx = xh - xi, sg = gh - gi;
+                        s2[0] = fma(sx, sx, s2[0]);
+                        s2[1] = fma(sx, sg, s2[1]);
+                    }
+                    reduce_sync<2>(k, c, s2);
+                    const double a = s2[0] / (s2[1] + 10 * kEps);
+                    project_pass(c.T, k.gtid, k.gstride, k.sm.scratch,
+                                 [&](int i) {
+                                     const double xh = ld_cg(xk + i) - af * ld_cg(p + i);
+                                     const double gh = ld_cg(gk + i) - af * ld_cg(Ap + i);
+                                     return xh - a * gh;
+                                 },
+                                 [&](int i, double, double pr) { xn[i] = pr; });
+                    barrier_only(k);
+                    gemv_phase(k, c, xn, [&](int r, double s) { gn[r] = s + b[r]; });
+                    k.mv += 1;
+                    barrier_only(k);
+                    if (hit_max(k, c)) break;
+                    project_pass(c.T, k.gtid, k.gstride, k.sm.scratch, [&](int i) { return ld_cg(xn + i); },
+                                 [&](int i, double t, double pr) { p[i] = is_close(t, pr) ? ld_cg(gn + i) : 0.0; });
+                    abb_lazy = true;
+                }
+            } else {
+                // proportioning step :1164-1182
+                if (abb_lazy) {   // alpha_bb of the previous iteration, evaluated only when needed
+                    double s1[1] = {0.0};
+                    CCQP_ELEMS(i) { const double dv = ld_cg(xk + i) - ld_cg(xn + i); w[i] = dv; s1[0] = fma(dv, dv, s1[0]); }
+                    reduce_sync<1>(k, c, s1);
+                    double s2[1] = {0.0};
+                    gemv_phase(k, c, w, [&](int r, double s) { s2[0] = fma(ld_cg(w + r), s, s2[0]); });
+                    reduce_sync<1>(k, c, s2);
+                    abb = s1[0] / (s2[0] + 10 * kEps);
+                }
+                project_pass(c.T, k.gtid, k.gstride, k.sm.scratch,
+                             [&](int i) { return ld_cg(xk + i) - abb * ld_cg(gk + i); },
+                             [&](int i, double, double pr) { xn[i] = pr; });
+                abb_lazy = true;
+                k.mv += 1;            // gk = A xk + b is re-evaluated by the reference (:1174); same value
+                barrier_only(k);
+                if (hit_max(k, c)) break;
+                project_pass(c.T, k.gtid, k.gstride, k.sm.scratch, [&](int i) { return ld_cg(xn + i); },
+                             [&](int i, double t, double pr) { p[i] = is_close(t, pr) ? ld_cg(gn + i) : 0.0; });   // stale gn (:1181)
+            }
+            double r1[1] = {residual_partial(k, c, cs, [&](int i) { return ld_cg(xn + i); }, [&](int i) { return ld_cg(gn + i); })};
+            reduce_sync<1>(k, c, r1);
+            res = sqrt(r1[0]);
+            k.iters += 1;
+            if (res < c.tol) break;
+            swap_ptr(xk, xn);
+            swap_ptr(gk, gn);
+        }
+    }
+    barrier_only(k);
+    finish(k, c, xn, res, status);
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel
+// ------------------------------------------------------------------------------------------
+template <int OP>
+__global__ void __launch_bounds__(kDenseThreads, 1) dense_kernel(const DenseCtx c) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Kst k;
+    {
+        unsigned char* q = smem_raw;
+        k.sm.vbuf[0] = reinterpret_cast<double*>(q); q += (size_t)c.CW * 8;
+        k.sm.vbuf[1] = reinterpret_cast<double*>(q); q += (size_t)c.CW * 8;
+        k.sm.psum = reinterpret_cast<double*>(q); q += (size_t)c.rows_max * c.nseg * 8;
+        k.sm.scratch = reinterpret_cast<double*>(q); q += kMaxRed * 32 * 8;
+        k.sm.ascratch = reinterpret_cast<unsigned long long*>(q); q += 32 * 8;
+        k.sm.mbar = reinterpret_cast<uint64_t*>(q);
+    }
+    k.gs.counter = c.bar_counter;
+    k.gs.abort = c.abort_flag;
+    k.gs.target = 0;
+    k.gtid = blockIdx.x * kDenseThreads + threadIdx.x;
+    k.gstride = gridDim.x * kDenseThreads;
+    k.r0 = c.row0 + (int)(((long long)c.nrows * blockIdx.x) / gridDim.x);
+    k.r1 = c.row0 + (int)(((long long)c.nrows * (blockIdx.x + 1)) / gridDim.x);
+    k.par[0] = k.par[1] = 0u;
+    k.redbuf = 0;
+    k.mv = k.gemv = k.iters = k.draws = 0;
+    if (threadIdx.x == 0) {
+        mbar_init(&k.sm.mbar[0], 1);
+        mbar_init(&k.sm.mbar[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if constexpr (OP == OP_PGD || OP == OP_BBPGD || OP == OP_BBPGDF) solve_pgd_family<OP>(k, c);
+    else if constexpr (OP == OP_SPG) solve_spg(k, c);
+    else if constexpr (OP == OP_APGD) solve_apgd<false>(k, c);
+    else if constexpr (OP == OP_APGD_AR) solve_apgd<true>(k, c);
+    else if constexpr (OP == OP_MPRGP) solve_mprgp(k, c);
+    else if constexpr (OP == OP_GEMV) {
+        gemv_phase(k, c, c.hook_in, [&](int r, double s) { c.hook_out[r - c.row0] = s; });
+    } else if constexpr (OP == OP_PROJECT) {
+        project_pass(c.T, k.gtid, k.gstride, k.sm.scratch, [&](int i) { return c.hook_in[i]; },
+                     [&](int i, double, double p) { c.hook_out[i] = p; });
+    } else if constexpr (OP == OP_NORMAL) {
+        normal_pass(c.T, k.gtid, k.gstride, k.sm.scratch, [&](int i) { return c.hook_in[i]; }, c.hook_out);
+    }
+}
+
+}  // namespace ccqp

@@ -1,0 +1,183 @@
+/*
+ * ccqp_b200.h -- C ABI of the B200-native CCQP projected-gradient hot path.
+ *
+ * This is the drop-in boundary for the path BASELINE.json's north_star names: the loop bodies of
+ * the reference's solvers (the per-iteration fp64 A@x mat-vec, the convex projection, the
+ * step-length dot products and residual reductions).  The reference is pure Python; each entry
+ * point below names the reference interface it replaces (file:line under /root/reference) and
+ * INTEGRATION.md shows the ctypes stub a maintainer of the reference would add.
+ *
+ * Rules of the boundary
+ *   - extern "C", plain pointers and sizes, no C++/torch types, no exceptions: every call returns a
+ *     ccqp_status; ccqp_status_string() gives text.
+ *   - Every data pointer is either a HOST or a DEVICE pointer, named by a ccqp_memtype argument.
+ *     Host buffers are copied by the library (pinned host memory gives asynchronous copies).
+ *   - All reals are IEEE fp64.  Matrices are row-major (C order) with leading dimension lda.
+ *   - One handle per host thread; a handle owns one CUDA device, one stream and its workspaces.
+ *   - There is no CPU fallback: with no usable device ccqp_create() fails with
+ *     CCQP_ERR_NO_DEVICE.
+ */
+#ifndef CCQP_B200_H
+#define CCQP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CCQP_ABI_VERSION 1
+
+typedef enum ccqp_status {
+    CCQP_OK = 0,
+    CCQP_ERR_INVALID_ARG = 1,            /* bad shape / null pointer / unknown id                   */
+    CCQP_ERR_NO_DEVICE = 2,              /* no CUDA device, or not an sm_100 part                   */
+    CCQP_ERR_CUDA = 3,                   /* a CUDA runtime call failed (see ccqp_last_error)        */
+    CCQP_ERR_UNSUPPORTED = 4,            /* valid request that this build does not implement        */
+    CCQP_ERR_NOT_READY = 5,              /* solve before set_matrix / set_projection                */
+    CCQP_ERR_NORMAL_NOT_IMPLEMENTED = 6, /* MPRGP reached normal_vector of a reference Cone block:
+                                            the reference raises NotImplementedError there
+                                            (solution_spaces.py:465)                                */
+    CCQP_ERR_UNIFORMS_EXHAUSTED = 7,     /* SPG consumed every supplied uniform sample              */
+    CCQP_ERR_RANGE = 8,                  /* SPG step bound is NaN: np.random.uniform raises
+                                            OverflowError there (solvers.py:959)                    */
+    CCQP_ERR_DEVICE_TIMEOUT = 9,         /* an in-kernel barrier timed out (kernel aborted)         */
+    CCQP_ERR_COMM = 10                   /* multi-GPU exchange setup failed                         */
+} ccqp_status;
+
+typedef enum ccqp_memtype { CCQP_MEM_HOST = 0, CCQP_MEM_DEVICE = 1 } ccqp_memtype;
+
+/* Leaf projection operators.  One block == one leaf operator of the reference; a table with
+ * several blocks is the reference's DisjointProjOp (solution_spaces.py:495-560).             */
+typedef enum ccqp_block_kind {
+    CCQP_BLOCK_IDENTITY = 0, /* IdentityProjOp   solution_spaces.py:77   params: none               */
+    CCQP_BLOCK_LOWER = 1,    /* LowerBoundProjOp solution_spaces.py:128  params: lb[dim]            */
+    CCQP_BLOCK_UPPER = 2,    /* UpperBoundProjOp solution_spaces.py:204  params: ub[dim]            */
+    CCQP_BLOCK_BOX = 3,      /* BoxProjOp        solution_spaces.py:280  params: lb[dim], ub[dim]   */
+    CCQP_BLOCK_SPHERE = 4,   /* SphereProjOp     solution_spaces.py:369  params: radius             */
+    CCQP_BLOCK_CONE_REF = 5, /* ConeProjOp       solution_spaces.py:438  params: aspect ratio mu;
+                                bug-compatible with the reference ("this projection op is bugged") */
+    CCQP_BLOCK_SOC = 6       /* extension: the correct second-order-cone projection {|u| <= mu z};
+                                not in the reference, parity unpinned                               */
+} ccqp_block_kind;
+
+typedef struct ccqp_block {
+    int32_t kind;      /* ccqp_block_kind                                  */
+    int32_t reserved;  /* must be 0                                        */
+    int64_t offset;    /* first element of the block; blocks tile [0,n)    */
+    int64_t dim;       /* embedded_dimension of the leaf operator          */
+    int64_t param_off; /* offset of the block's parameters in params[]     */
+} ccqp_block;
+
+/* Solvers.  The ids are the rows of SURVEY.md section 8(a). */
+typedef enum ccqp_solver {
+    CCQP_SOLVER_PGD = 0,     /* CCQPSolverPGD.solve                 solvers.py:94-170    */
+    CCQP_SOLVER_APGD = 1,    /* CCQPSolverAPGD.solve                solvers.py:220-343   */
+    CCQP_SOLVER_APGD_AR = 2, /* CCQPSolverAPGDAntiRelaxation.solve  solvers.py:393-533   */
+    CCQP_SOLVER_BBPGD = 3,   /* CCQPSolverBBPGD.solve               solvers.py:583-669   */
+    CCQP_SOLVER_BBPGDF = 4,  /* CCQPSolverBBPGDf.solve              solvers.py:719-819   */
+    CCQP_SOLVER_SPG = 5,     /* CCQPSolverSPG.solve                 solvers.py:878-975   */
+    CCQP_SOLVER_MPRGP = 6    /* CCQPSolverMPRGP.solve               solvers.py:1026-1200 */
+} ccqp_solver;
+
+/* Constructor arguments of the reference's solver classes (solvers.py:81, :208, :571, :856). */
+typedef struct ccqp_params {
+    double tol;       /* desired_residual_tol                                                   */
+    double max_mv;    /* max_matrix_vector_multiplications; +inf allowed (the reference default) */
+    double step_size; /* PGD only (solvers.py:81), default 0.01                                  */
+    double tau;       /* SPG (solvers.py:856), default 0.5                                       */
+    double sigma1;    /* SPG, default 0.01                                                       */
+    double sigma2;    /* SPG, default 0.5                                                        */
+    int32_t m;        /* SPG non-monotone window, default 5 (1..64)                              */
+    int32_t reserved;
+} ccqp_params;
+
+/* Result fields of the reference (solvers.py:163-168) plus accounting for the roofline. */
+typedef struct ccqp_result {
+    double residual;       /* solution_residual (NaN where the reference would raise NameError) */
+    double gpu_seconds;    /* device time of the solve, CUDA events on the handle's stream       */
+    double hbm_bytes;      /* algorithmic bytes moved: gemv_count * (8 n_rows n + 16 n)          */
+    int64_t mv_count;      /* solution_num_matrix_vector_multiplications (the REPORTED count)    */
+    int64_t gemv_count;    /* mat-vec products actually executed on the device                   */
+    int64_t iterations;    /* outer iterations completed                                         */
+    int64_t uniforms_used; /* SPG: samples consumed from uniforms[]                              */
+    int32_t converged;     /* solution_converged = mv_count < max_mv                             */
+    int32_t status;        /* ccqp_status raised inside the kernel (0 = none)                    */
+    int64_t kernel_launches; /* kernels launched by the call                                     */
+} ccqp_result;
+
+typedef struct ccqp_handle ccqp_handle;
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+int ccqp_abi_version(void);
+const char* ccqp_status_string(int status);
+/* Text of the last CUDA error seen by this handle (empty string if none). */
+const char* ccqp_last_error(const ccqp_handle* h);
+
+/* Create a handle on CUDA device `device` (-1 = current device).  Fails with
+ * CCQP_ERR_NO_DEVICE when there is none: there is no CPU path behind this ABI. */
+ccqp_status ccqp_create(ccqp_handle** out, int device);
+ccqp_status ccqp_destroy(ccqp_handle* h);
+/* Use an existing cudaStream_t (e.g. torch's current stream) instead of the handle's own. */
+ccqp_status ccqp_set_stream(ccqp_handle* h, void* cuda_stream);
+/* Number of SMs of the handle's device and its memory clock/bus derived peak are not exposed;
+ * the kernel grid the dense solver will use is. */
+ccqp_status ccqp_get_info(const ccqp_handle* h, int32_t* sm_count, int32_t* dense_grid,
+                          int32_t* dense_threads, int64_t* dense_smem_bytes);
+
+/* ---- problem data -------------------------------------------------------------------------- */
+/* The Hessian.  Replaces the `A` argument of solve() (solvers.py:94); the reference touches A
+ * only through A.dot(v) (26 call sites).  `A` points at rows
+ * [row_begin, row_begin+n_rows) of the n x n matrix (row shard; single GPU: row_begin = 0,
+ * n_rows = n).  A DEVICE matrix is borrowed, not copied, and must outlive the solves.      */
+ccqp_status ccqp_set_matrix(ccqp_handle* h, const double* A, int64_t n, int64_t lda,
+                            int64_t row_begin, int64_t n_rows, int memtype);
+
+/* The feasible set.  Replaces the `convex_proj_op` argument of solve() (solvers.py:94) and the
+ * operator classes of solution_spaces.py.  blocks must tile [0,n) in order.  Host pointers. */
+ccqp_status ccqp_set_projection(ccqp_handle* h, const ccqp_block* blocks, int64_t n_blocks,
+                                const double* params, int64_t n_params);
+
+/* ---- the hot path -------------------------------------------------------------------------- */
+/* One whole solve on the device: replaces CCQPSolver{PGD,APGD,APGDAntiRelaxation,BBPGD,BBPGDf,
+ * SPG,MPRGP}.solve (solvers.py:94,220,393,583,719,878,1026).  b, x0 (nullable = zeros), uniforms
+ * and x_out use `memtype`.  uniforms[] is the U[0,1) stream SPG's np.random.uniform (solvers.py:959)
+ * would consume; ignored by the other solvers. */
+ccqp_status ccqp_solve(ccqp_handle* h, int solver, const ccqp_params* params, const double* b,
+                       const double* x0, const double* uniforms, int64_t n_uniforms, double* x_out,
+                       int memtype, ccqp_result* result);
+
+/* Many small independent box-constrained QPs, one CTA per problem, whole solver loop on the
+ * device.  Problem i is defined to equal
+ *     CCQPSolverX(tol,max_mv).solve(A[i], b[i], x0[i], BoxProjOp(n, lb[i], ub[i]))
+ * (solvers.py:94.. with solution_spaces.py:280).  A is [batch][n][n]; b, x0 (nullable), lb, ub,
+ * x_out are [batch][n]; uniforms is [batch][n_uniforms] (SPG); results is [batch] in HOST memory.
+ * Supported n: 1..64 (n = 64 is the tuned case). */
+ccqp_status ccqp_solve_batched(ccqp_handle* h, int solver, const ccqp_params* params, int64_t batch,
+                               int64_t n, const double* A, const double* b, const double* x0,
+                               const double* lb, const double* ub, const double* uniforms,
+                               int64_t n_uniforms, double* x_out, int memtype,
+                               ccqp_result* results, ccqp_result* summary);
+
+/* ---- unit-test hooks for the pieces of the path ---------------------------------------------- */
+/* y = A v for the handle's row shard (y has n_rows entries).  A.dot(v), solvers.py:133 etc. */
+ccqp_status ccqp_gemv(ccqp_handle* h, const double* v, double* y, int memtype);
+/* out = P(x): ProjOp.__call__, solution_spaces.py:125,200,276,363,431,484,553. */
+ccqp_status ccqp_project(ccqp_handle* h, const double* x, double* out, int memtype);
+/* out = normal_vector(x): solution_spaces.py:92,146,222,306,389,459,512. */
+ccqp_status ccqp_normal(ccqp_handle* h, const double* x, double* out, int memtype);
+
+/* ---- multi-GPU (row-sharded dense solves, one process per GPU) -------------------------------- */
+/* Each rank exports an opaque descriptor of its exchange buffer, the host side all-gathers the
+ * descriptors (torch.distributed), and every rank attaches the peers'.  After that ccqp_solve()
+ * exchanges vector slices and scalar partials inside the solver kernel through NVLink peer
+ * memory.  desc must hold CCQP_COMM_DESC_BYTES bytes. */
+#define CCQP_COMM_DESC_BYTES 128
+ccqp_status ccqp_comm_export(ccqp_handle* h, int rank, int world, int64_t n, void* desc);
+ccqp_status ccqp_comm_attach(ccqp_handle* h, const void* all_descs /* world * DESC_BYTES */);
+ccqp_status ccqp_comm_detach(ccqp_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CCQP_B200_H */

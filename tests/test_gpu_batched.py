@@ -1,0 +1,89 @@
+"""Batched mode (config 4) on the GPU against the oracle, problem by problem."""
+import numpy as np
+import pytest
+
+import problems as pr
+from helpers import make_solver
+from oracle import ccqp_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def make_batch(batch, n, seed0=0, mu=1.0):
+    A = np.empty((batch, n, n))
+    b = np.empty((batch, n))
+    for i in range(batch):
+        A[i], b[i] = pr.shift_problem(n, seed0 + i, mu)
+    rng = np.random.default_rng(1234 + seed0)
+    lb = -1.0 - 0.2 * rng.random((batch, n))
+    ub = 1.0 + 0.2 * rng.random((batch, n))
+    return A, b, lb, ub
+
+
+def oracle_one(solver, A, b, lb, ub, x0, tol, max_mv, step, seed, K):
+    tab = pr.Table().add(pr.BOX, A.shape[0], lb, ub)
+    return orc.solve(solver, A, b, x0=x0, blocks=tab.blocks, params=tab.params, tol=tol, max_mv=max_mv, step_size=step,
+                     uniforms=pr.spg_uniforms(seed, K))
+
+
+@pytest.mark.parametrize("solver", [pr.PGD, pr.APGD, pr.APGD_AR, pr.BBPGD, pr.BBPGDF, pr.SPG])
+@pytest.mark.parametrize("n", [64, 32, 17, 5])
+def test_batched_matches_oracle(solver, n):
+    batch, tol, max_mv, step, K = 48, 1e-8, 5000, 0.1, 512
+    A, b, lb, ub = make_batch(batch, n)
+    x0 = None if n != 32 else 0.5 * np.random.default_rng(3).standard_normal((batch, n))
+    s = make_solver(solver, tol, max_mv, step)
+    s.solve_batched(A, b, lb, ub, x0=x0, seeds=np.arange(batch), n_uniforms=K)
+    for i in range(batch):
+        o = oracle_one(solver, A[i], b[i], lb[i], ub[i], None if x0 is None else x0[i], tol, max_mv, step, i, K)
+        assert bool(s.solution_converged[i]) == o["converged"]
+        mv = int(s.solution_num_matrix_vector_multiplications[i])
+        assert abs(mv - o["mv"]) <= max(1, round(0.02 * o["mv"])), (i, mv, o["mv"])
+        if mv == o["mv"]:
+            assert np.linalg.norm(s.solution[i] - o["solution"]) <= 1e-9 * max(np.linalg.norm(o["solution"]), 1e-300)
+            assert abs(s.solution_residual[i] - o["residual"]) <= 1e-6 * o["residual"] + 1e-14
+
+
+def test_batched_mvlimit_and_device_tensors():
+    import torch
+    batch, n = 40, 64
+    A, b, lb, ub = make_batch(batch, n, seed0=100, mu=0.01)
+    s = make_solver(pr.BBPGD, 1e-12, 9)
+    s.solve_batched(A, b, lb, ub)
+    assert not s.solution_converged.any() and (s.solution_num_matrix_vector_multiplications == 9).all()
+    host = np.array(s.solution)
+    s.solve_batched(torch.from_numpy(A).cuda(), torch.from_numpy(b).cuda(), torch.from_numpy(lb).cuda(),
+                    torch.from_numpy(ub).cuda())
+    assert s.solution.is_cuda and np.array_equal(s.solution.cpu().numpy(), host)
+
+
+def test_batched_large_properties():
+    """Size-independent properties on a batch larger than one wave of CTAs: every problem
+    converged, feasible, and a fixed point of the projected-gradient map to the tolerance."""
+    import torch
+    batch, n, tol = 8192, 64, 1e-8
+    g = torch.Generator(device="cuda").manual_seed(0)
+    G = torch.randn((batch, n, n), generator=g, device="cuda", dtype=torch.float64)
+    A = G @ G.transpose(1, 2) / n + torch.eye(n, device="cuda", dtype=torch.float64)
+    xs = 1 - 4 * torch.rand((batch, n), generator=g, device="cuda", dtype=torch.float64)
+    b = -(A @ xs.unsqueeze(-1)).squeeze(-1)
+    lb = -torch.ones_like(b)
+    ub = torch.ones_like(b)
+    for solver in (pr.BBPGD, pr.SPG):
+        s = make_solver(solver, tol, 5000)
+        s.solve_batched(A, b, lb, ub, n_uniforms=256)
+        x = s.solution
+        assert s.solution_converged.all()
+        assert bool(((x >= lb) & (x <= ub)).all())
+        grad = (A @ x.unsqueeze(-1)).squeeze(-1) + b
+        fix = x - torch.clamp(x - 1e-6 * grad, lb, ub)
+        res = fix.norm(dim=1) / (3 * n * 1e-6)
+        if solver == pr.BBPGD:
+            assert float(res.max()) < tol * 1.001
+        else:
+            assert float(res.max()) < 1e-6
+    # problems are independent: a permuted batch gives permuted, bit-identical answers
+    perm = torch.randperm(batch, device="cuda")
+    s1 = make_solver(pr.BBPGD, tol, 5000).solve_batched(A, b, lb, ub)
+    s2 = make_solver(pr.BBPGD, tol, 5000).solve_batched(A[perm].contiguous(), b[perm].contiguous(), lb, ub)
+    assert torch.equal(s1.solution[perm], s2.solution)

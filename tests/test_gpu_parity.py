@@ -1,0 +1,200 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the public API and
+therefore through the C-ABI, against (a) the golden fixtures generated from the live reference
+and (b) the oracle on the same seeded inputs.
+
+Tolerances (north_star): solution within 1e-9 relative, same converged flag, mat-vec count within
+2 % (reduction order differs).  Elementwise projections are bit-exact."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import problems as pr
+from helpers import op_from_table, run_gpu, make_solver
+from oracle import ccqp_oracle as orc
+from test_oracle_golden import META, PROJ, TABLES, case_inputs, check_against_golden
+
+pytestmark = pytest.mark.gpu
+
+
+# ---- pieces of the path ------------------------------------------------------------------------
+@pytest.mark.parametrize("name", sorted(TABLES))
+def test_projection_matches_reference_golden(name):
+    tab = TABLES[name]()
+    op = op_from_table(tab)
+    elementwise = name in ("identity", "box", "lower", "upper")
+    for x, px in zip(PROJ[name + "/x"], PROJ[name + "/px"]):
+        got = np.asarray(op(x.copy()))
+        if elementwise:
+            assert np.array_equal(got, px)            # bit-exact (sign of zero aside: == treats them equal)
+        else:
+            np.testing.assert_allclose(got, px, rtol=1e-15, atol=1e-300)
+
+
+@pytest.mark.parametrize("name", sorted(n for n in TABLES if not n.startswith("cone")))
+def test_normal_vector_matches_reference_golden(name):
+    tab = TABLES[name]()
+    op = op_from_table(tab)
+    for x, px, nv, nvp in zip(PROJ[name + "/x"], PROJ[name + "/px"], PROJ[name + "/nv"], PROJ[name + "/nvp"]):
+        np.testing.assert_allclose(np.asarray(op.normal_vector(x.copy())), nv, rtol=1e-15, atol=0)
+        np.testing.assert_allclose(np.asarray(op.normal_vector(px.copy())), nvp, rtol=1e-15, atol=0)
+
+
+def test_cone_normal_raises_like_reference():
+    from ccqppy_b200 import solution_spaces as ss
+    with pytest.raises(NotImplementedError):
+        ss.ConeProjOp(3).normal_vector(np.ones(3))
+
+
+def test_soc_projection_matches_oracle_extension():
+    rng = np.random.default_rng(5)
+    for tab in (pr.soc3_table(30, 0.5), pr.Table().add(pr.SOC, 40, 0.7)):
+        op = op_from_table(tab)
+        for _ in range(10):
+            x = 2 * rng.standard_normal(tab.n)
+            np.testing.assert_allclose(np.asarray(op(x)), orc.project(tab.blocks, tab.params, x), rtol=2e-15, atol=1e-300)
+            np.testing.assert_allclose(np.asarray(op.normal_vector(np.asarray(op(x)))),
+                                       orc.normal_vector(tab.blocks, tab.params, orc.project(tab.blocks, tab.params, x)),
+                                       rtol=1e-12, atol=1e-15)
+
+
+@pytest.mark.parametrize("n", [1, 3, 64, 127, 300, 1000, 1023, 2048, 4100, 8200, 16500])
+def test_gemv_matches_numpy(n):
+    import ctypes
+    from ccqppy_b200 import _capi
+    rng = np.random.default_rng(n)
+    A = rng.standard_normal((n, n))
+    v = rng.standard_normal(n)
+    h = _capi.Handle()
+    pa, ma, _ = _capi.f64_ptr(A)
+    _capi.check(h.h, h.lib.ccqp_set_matrix(h.h, pa, n, n, 0, n, ma))
+    y = np.empty(n)
+    pv, mv, _ = _capi.f64_ptr(v)
+    py, _, _ = _capi.f64_ptr(y)
+    _capi.check(h.h, h.lib.ccqp_gemv(h.h, pv, py, mv))
+    ref = A @ v
+    scale = np.abs(A) @ np.abs(v)
+    assert np.max(np.abs(y - ref) / scale) < 4e-16 * max(4, np.log2(n + 1))
+    h.close()
+
+
+# ---- whole solves against the reference's goldens ------------------------------------------------
+@pytest.mark.parametrize("c", META, ids=[c["name"] for c in META])
+def test_solver_matches_reference_golden(c):
+    A, b, tab, x0 = case_inputs(c)
+    out = run_gpu(c["solver"], A, b, tab, x0=x0, tol=c["tol"], max_mv=c["max_mv"], step=c["step"],
+                  spg_seed=c["spg_seed"])
+    check_against_golden(c, out)
+    if c["converged"] and out["mv"] == c["mv"]:
+        gold_res = float.fromhex(c["residual"])
+        assert abs(out["residual"] - gold_res) <= 1e-6 * abs(gold_res) + 1e-12
+
+
+def test_reference_test_matrix():
+    """The reference's own test (tests/test_module.py:19-67): every solver on the five analytic
+    problems, converged and within 1e-5 of the exact solution."""
+    from ccqppy_b200 import problem_suite, solvers
+    probs = [problem_suite.UnconstrainedSPD1(), problem_suite.UnconstrainedSPD2(), problem_suite.BoxConstrainedSPD(),
+             problem_suite.ThinBoxConstrainedSPD(), problem_suite.ActiveBoxConstrainedSPD()]
+    makers = [lambda: solvers.CCQPSolverPGD(1e-8, 10000, 0.1), lambda: solvers.CCQPSolverAPGD(1e-8, 10000),
+              lambda: solvers.CCQPSolverAPGDAntiRelaxation(1e-8, 10000), lambda: solvers.CCQPSolverBBPGD(1e-8, 10000),
+              lambda: solvers.CCQPSolverBBPGDf(1e-8, 10000), lambda: solvers.CCQPSolverSPG(1e-8, 10000),
+              lambda: solvers.CCQPSolverMPRGP(1e-8, 10000), lambda: solvers.CCQPSolverMPRGPBB(1e-8, 10000)]
+    for p in probs:
+        for mk in makers:
+            r = mk().solve(p.A, p.b, convex_proj_op=p.convex_proj_op)
+            assert r.solution_converged
+            assert np.linalg.norm(r.solution - p.exact_solution) < 1e-5
+
+
+def test_readme_example_and_rng_side_effect(capsys):
+    """README.md:30-51.  Also: the global NumPy RNG must end where the reference leaves it."""
+    from ccqppy_b200 import solvers, solution_spaces as ss
+    A = np.array([[2, -1, 0], [-1, 2, -1], [0, -1, 2]])
+    exact_x = np.array([1, 0, 1])
+    b = -A.dot(exact_x)
+    op = ss.BoxProjOp(3, np.array([-2, -2, -4]), np.array([2, 2, 5]))
+    np.random.seed(0)
+    result = solvers.CCQPSolverSPG(1e-10, 5000).solve(A, b, convex_proj_op=op)
+    after_gpu = np.random.random_sample()
+    assert capsys.readouterr().out == "solving SPG\n"
+    tab = pr.Table().add(pr.BOX, 3, np.array([-2., -2., -4.]), np.array([2., 2., 5.]))
+    np.random.seed(0)
+    o = orc.solve(pr.SPG, A, b, blocks=tab.blocks, params=tab.params, tol=1e-10, max_mv=5000)
+    after_ref = np.random.random_sample()
+    assert result.solution_converged and result.solution_num_matrix_vector_multiplications == o["mv"] == 92
+    assert after_gpu == after_ref
+    assert np.linalg.norm(result.solution - exact_x) < 1e-9
+    assert isinstance(result.solution_time, float) and result.solution_time > 0
+
+
+def test_mprgp_with_reference_cone_raises():
+    from ccqppy_b200 import solvers, solution_spaces as ss
+    A, b = pr.shift_problem(30, 0)
+    op = ss.DisjointProjOp(*[ss.ConeProjOp(3)] * 10)
+    s = solvers.CCQPSolverMPRGP(1e-6, 100)
+    s.quiet = True
+    with pytest.raises(NotImplementedError):
+        s.solve(A, b, convex_proj_op=op)
+
+
+def test_soc_cones_extension_against_oracle():
+    """Config 5 flavour: contact-style friction cones (correct SOC projection; oracle = our CPU
+    restatement, parity unpinned by the reference)."""
+    n = 300
+    A, b = pr.shift_problem(n, 2)
+    tab = pr.soc3_table(n, 0.5)
+    for solver in (pr.APGD, pr.BBPGD, pr.SPG, pr.MPRGP):
+        o = orc.solve(solver, A, b, blocks=tab.blocks, params=tab.params, tol=1e-6, max_mv=3000,
+                      uniforms=pr.spg_uniforms(3, 3000))
+        g = run_gpu(solver, A, b, tab, tol=1e-6, max_mv=3000, spg_seed=3)
+        assert g["converged"] == o["converged"]
+        assert abs(g["mv"] - o["mv"]) <= max(1, round(0.02 * o["mv"]))
+        if g["mv"] == o["mv"]:
+            assert np.linalg.norm(g["solution"] - o["solution"]) <= 1e-9 * np.linalg.norm(o["solution"])
+
+
+def test_torch_device_inputs_are_used_in_place():
+    import torch
+    n = 512
+    A, b = pr.shift_problem(n, 9)
+    tab = pr.box_table(n)
+    ref = run_gpu(pr.BBPGD, A, b, tab, tol=1e-7, max_mv=500)
+    Ad, bd = torch.from_numpy(A).cuda(), torch.from_numpy(b).cuda()
+    s = make_solver(pr.BBPGD, 1e-7, 500)
+    s.solve(Ad, bd, convex_proj_op=op_from_table(tab))
+    assert s.solution.is_cuda
+    assert np.array_equal(s.solution.cpu().numpy(), ref["solution"])
+    assert s.solution_num_matrix_vector_multiplications == ref["mv"]
+    # pinned host tensors go through the same host path as NumPy arrays
+    Ap, bp = torch.from_numpy(A).pin_memory(), torch.from_numpy(b).pin_memory()
+    s.solve(Ap, bp, convex_proj_op=op_from_table(tab))
+    assert np.array_equal(np.asarray(s.solution), ref["solution"])
+
+
+def test_determinism_run_to_run():
+    n = 1500
+    A, b = pr.shift_problem(n, 4, 0.01)
+    tab = pr.mixed_table(n)
+    outs = [run_gpu(pr.SPG, A, b, tab, tol=1e-6, max_mv=2000, spg_seed=2) for _ in range(3)]
+    for o in outs[1:]:
+        assert o["mv"] == outs[0]["mv"] and np.array_equal(o["solution"], outs[0]["solution"])
+
+
+@pytest.mark.parametrize("solver", [pr.PGD, pr.APGD, pr.BBPGD, pr.SPG, pr.MPRGP])
+def test_dense_4096_config2_against_oracle(solver):
+    """Config 2: random dense SPD n=4096, box constraints, all five solvers, vs the oracle on the
+    same inputs (the oracle finishes in seconds at this size)."""
+    n = 4096
+    A, b = pr.shift_problem(n, 0)
+    tab = pr.box_table(n)
+    step = 1.0 / np.abs(A).sum(axis=1).max()
+    max_mv = 300
+    o = orc.solve(solver, A, b, blocks=tab.blocks, params=tab.params, tol=1e-5, max_mv=max_mv, step_size=step,
+                  uniforms=pr.spg_uniforms(0, max_mv))
+    g = run_gpu(solver, A, b, tab, tol=1e-5, max_mv=max_mv, step=step, spg_seed=0)
+    assert g["converged"] == o["converged"]
+    assert abs(g["mv"] - o["mv"]) <= max(1, round(0.02 * o["mv"])), (g["mv"], o["mv"])
+    if g["mv"] == o["mv"]:
+        assert np.linalg.norm(g["solution"] - o["solution"]) <= 1e-9 * np.linalg.norm(o["solution"])
