@@ -21,7 +21,7 @@ ERR_RANGE = 8
 
 EXPORTS = ["ccqp_abi_version", "ccqp_status_string", "ccqp_last_error", "ccqp_create", "ccqp_destroy",
            "ccqp_set_stream", "ccqp_get_info", "ccqp_set_matrix", "ccqp_set_projection", "ccqp_solve",
-           "ccqp_solve_batched", "ccqp_gemv", "ccqp_project", "ccqp_normal", "ccqp_comm_export",
+           "ccqp_solve_batched", "ccqp_gemv", "ccqp_gemv_timed", "ccqp_project", "ccqp_normal", "ccqp_comm_export",
            "ccqp_comm_attach", "ccqp_comm_detach"]
 
 
@@ -77,6 +77,7 @@ def load():
     lib.ccqp_solve_batched.argtypes = [vp, i32, C.POINTER(Params), i64, i64, dp, dp, dp, dp, dp, dp, i64, dp, i32,
                                        C.POINTER(Result), C.POINTER(Result)]
     lib.ccqp_gemv.argtypes = [vp, dp, dp, i32]
+    lib.ccqp_gemv_timed.argtypes = [vp, dp, dp, i32, C.POINTER(C.c_double)]
     lib.ccqp_project.argtypes = [vp, dp, dp, i32]
     lib.ccqp_normal.argtypes = [vp, dp, dp, i32]
     lib.ccqp_comm_export.argtypes = [vp, i32, i32, i64, vp]

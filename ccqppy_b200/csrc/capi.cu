@@ -6,6 +6,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -110,6 +111,9 @@ Tiling choose_tiling(const ccqp_handle* h) {
     t.rows_max = (int)((nrows + t.grid - 1) / t.grid) + 1;
     t.CW = (int)std::min<long long>(8192, round_up(n, 128));
     t.SW = std::min(2048, t.CW);
+    // tuning overrides (multiples of 128; SW must divide CW)
+    if (const char* e = getenv("CCQP_CW")) t.CW = (int)std::min<long long>(atoi(e), round_up(n, 128));
+    if (const char* e = getenv("CCQP_SW")) t.SW = std::min(atoi(e), t.CW);
     for (;;) {
         t.np = (int)((n + t.CW - 1) / t.CW);
         const int spp_full = t.CW / t.SW;
@@ -146,6 +150,7 @@ void fill_ctx(ccqp_handle* h, DenseCtx& c, const Tiling& t) {
     c.out = h->out_dev.as<DenseOut>();
     c.CW = t.CW; c.SW = t.SW; c.np = t.np; c.nseg = t.nseg; c.rows_max = t.rows_max;
     c.evict_first = ((double)h->nrows * (double)h->n * 8.0 > 96.0 * 1024 * 1024) ? 1 : 0;
+    if (const char* e = getenv("CCQP_EVICT_FIRST")) c.evict_first = atoi(e);
 }
 
 template <int OP>
@@ -155,7 +160,7 @@ ccqp_status launch_dense(ccqp_handle* h, DenseCtx& c, const Tiling& t, bool coop
         CU(h, cudaFuncSetAttribute(dense_kernel<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
         configured = 220 * 1024;
     }
-    CU(h, cudaMemsetAsync(h->flags.p, 0, 64, h->stream));
+    if (cooperative) CU(h, cudaMemsetAsync(h->flags.p, 0, 64, h->stream));   // barrier counter
     void* args[] = {&c};
     if (cooperative)
         CU(h, cudaLaunchCooperativeKernel((const void*)dense_kernel<OP>, dim3(t.grid), dim3(kDenseThreads), args, t.smem, h->stream));
@@ -166,6 +171,9 @@ ccqp_status launch_dense(ccqp_handle* h, DenseCtx& c, const Tiling& t, bool coop
 }
 
 ccqp_status launch_by_solver(ccqp_handle* h, int solver, DenseCtx& c, const Tiling& t) {
+#ifdef CCQP_SWEEP_BUILD
+    return CCQP_ERR_UNSUPPORTED;   // tuning build: only the mat-vec hook is compiled
+#else
     switch (solver) {
         case CCQP_SOLVER_PGD: return launch_dense<OP_PGD>(h, c, t, true);
         case CCQP_SOLVER_APGD: return launch_dense<OP_APGD>(h, c, t, true);
@@ -176,6 +184,7 @@ ccqp_status launch_by_solver(ccqp_handle* h, int solver, DenseCtx& c, const Tili
         case CCQP_SOLVER_MPRGP: return launch_dense<OP_MPRGP>(h, c, t, true);
     }
     return CCQP_ERR_INVALID_ARG;
+#endif
 }
 
 bool params_ok(const ccqp_params* p, int solver) {
@@ -432,6 +441,27 @@ static ccqp_status run_hook(ccqp_handle* h, int op, const double* in, double* ou
 ccqp_status ccqp_gemv(ccqp_handle* h, const double* v, double* y, int memtype) {
     if (!h) return CCQP_ERR_INVALID_ARG;
     return run_hook(h, OP_GEMV, v, y, h->n, h->nrows, memtype);
+}
+ccqp_status ccqp_gemv_timed(ccqp_handle* h, const double* v_dev, double* y_dev, int repeats, double* seconds) {
+    if (!h || !v_dev || !y_dev || repeats <= 0 || !seconds) return CCQP_ERR_INVALID_ARG;
+    if (!h->dA) return CCQP_ERR_NOT_READY;
+    CU(h, cudaSetDevice(h->device));
+    ccqp_status st = ensure_work(h);
+    if (st != CCQP_OK) return st;
+    const Tiling t = choose_tiling(h);
+    DenseCtx c;
+    fill_ctx(h, c, t);
+    c.hook_in = v_dev; c.hook_out = y_dev;
+    if ((st = launch_dense<OP_GEMV>(h, c, t, false)) != CCQP_OK) return st;   // warm-up
+    CU(h, cudaEventRecord(h->ev0, h->stream));
+    for (int i = 0; i < repeats; ++i)
+        if ((st = launch_dense<OP_GEMV>(h, c, t, false)) != CCQP_OK) return st;
+    CU(h, cudaEventRecord(h->ev1, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    float ms = 0.f;
+    CU(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    *seconds = ms * 1e-3 / repeats;
+    return CCQP_OK;
 }
 ccqp_status ccqp_project(ccqp_handle* h, const double* x, double* out, int memtype) {
     if (!h) return CCQP_ERR_INVALID_ARG;

@@ -23,9 +23,15 @@
 
 namespace ccqp {
 
-constexpr int kDenseThreads = 512;
+#ifndef CCQP_DENSE_THREADS
+#define CCQP_DENSE_THREADS 512
+#endif
+#ifndef CCQP_UNROLL
+#define CCQP_UNROLL 4
+#endif
+constexpr int kDenseThreads = CCQP_DENSE_THREADS;
 constexpr int kDenseWarps = kDenseThreads / 32;
-constexpr int kUnroll = 8;            // 256-bit loads in flight per lane
+constexpr int kUnroll = CCQP_UNROLL;  // 256-bit loads in flight per lane
 constexpr int kMaxRed = 8;            // doubles per grid reduction
 constexpr int kMaxWindow = 64;        // SPG non-monotone window
 

@@ -162,6 +162,9 @@ ccqp_status ccqp_solve_batched(ccqp_handle* h, int solver, const ccqp_params* pa
 /* ---- unit-test hooks for the pieces of the path ---------------------------------------------- */
 /* y = A v for the handle's row shard (y has n_rows entries).  A.dot(v), solvers.py:133 etc. */
 ccqp_status ccqp_gemv(ccqp_handle* h, const double* v, double* y, int memtype);
+/* Measurement hook: `repeats` back-to-back mat-vec kernels on device-resident v (n entries, padded
+ * by the caller to n+64 zeros) and y; returns the mean device time per launch (CUDA events). */
+ccqp_status ccqp_gemv_timed(ccqp_handle* h, const double* v_dev, double* y_dev, int repeats, double* seconds);
 /* out = P(x): ProjOp.__call__, solution_spaces.py:125,200,276,363,431,484,553. */
 ccqp_status ccqp_project(ccqp_handle* h, const double* x, double* out, int memtype);
 /* out = normal_vector(x): solution_spaces.py:92,146,222,306,389,459,512. */

@@ -200,6 +200,35 @@ def run_oracle(c, A, b, tab, x0, explicit_uniforms):
                      tol=c["tol"], max_mv=c["max_mv"], step_size=c["step"], uniforms=uni)
 
 
+class _Perturbed:
+    """A.dot with a relative perturbation of about one ulp per entry: a stand-in for "the same
+    product summed in another order" (what any other BLAS, or the GPU kernel, does)."""
+
+    def __init__(self, A, rng):
+        self.A = np.asarray(A, dtype=float)
+        self.absA = np.abs(self.A)
+        self.rng = rng
+
+    def dot(self, v):
+        y = self.A.dot(v)
+        return y + 2.2e-16 * (self.rng.random(y.shape) - 0.5) * self.absA.dot(np.abs(v))
+
+
+def stability_band(c, A, b, tab, x0, trials=6):
+    """Mat-vec counts of the oracle under rounding-level perturbations of the product.  A case
+    whose count never moves is "order stable" and is gated at the north_star tolerance; the
+    others (ill-conditioned Hessians, sign tests on rounding-level quantities) are chaotic in
+    the reference itself and are only checked against this band."""
+    rng = np.random.default_rng(12345)
+    counts = []
+    for _ in range(trials):
+        o = orc.solve(c["solver"], _Perturbed(A, rng), b, x0=x0, blocks=tab.blocks, params=tab.params,
+                      tol=c["tol"], max_mv=c["max_mv"], step_size=c["step"],
+                      uniforms=pr.spg_uniforms(c["spg_seed"], 20000))
+        counts.append(o["mv"])
+    return min(counts), max(counts)
+
+
 def gen_solvers():
     meta, arrays = [], {}
     for c in catalogue():
@@ -217,12 +246,14 @@ def gen_solvers():
                                  (c["name"], explicit, ref["mv"], ref["residual"], o["mv"],
                                   o["residual"], np.max(np.abs(o["solution"] - ref["solution"]))))
         entry = {k: v for k, v in c.items()}
+        lo, hi = stability_band(c, A, b, tab, x0)
         entry.update(mv=ref["mv"], converged=ref["converged"], residual=ref["residual"].hex(),
-                     gemv=o["gemv"], draws=o["draws"])
+                     gemv=o["gemv"], draws=o["draws"], mv_band=[min(lo, ref["mv"]), max(hi, ref["mv"])],
+                     order_stable=bool(lo == hi == ref["mv"]))
         meta.append(entry)
         arrays[c["name"]] = ref["solution"]
-        print("%-40s mv=%5d conv=%d res=%.3e gemv=%d" %
-              (c["name"], ref["mv"], ref["converged"], ref["residual"], o["gemv"]))
+        print("%-40s mv=%5d conv=%d res=%.3e gemv=%d band=%s" %
+              (c["name"], ref["mv"], ref["converged"], ref["residual"], o["gemv"], entry["mv_band"]))
     with open(os.path.join(GOLD, "solvers.json"), "w") as f:
         json.dump(meta, f, indent=0)
     np.savez_compressed(os.path.join(GOLD, "solvers.npz"), **arrays)
