@@ -139,13 +139,28 @@ def default_handle(device=-1):
     return _default[key]
 
 
+BLOCK_DTYPE = np.dtype([("kind", "<i4"), ("reserved", "<i4"), ("offset", "<i8"), ("dim", "<i8"), ("param_off", "<i8")])
+
+
+class BlockArray:
+    """ccqp_block[] backed by a NumPy structured array (fast to build for ~1e4 blocks)."""
+
+    def __init__(self, rows):
+        rows = np.asarray(rows, dtype=np.int64).reshape(-1, 4)
+        self.arr = np.zeros(rows.shape[0], dtype=BLOCK_DTYPE)
+        self.arr["kind"], self.arr["offset"], self.arr["dim"], self.arr["param_off"] = rows.T
+        self.ptr = self.arr.ctypes.data_as(C.POINTER(Block))
+
+    def __len__(self):
+        return self.arr.shape[0]
+
+    def __getitem__(self, k):
+        return self.ptr[k]
+
+
 def make_blocks(rows):
-    """rows: iterable of (kind, offset, dim, param_off) -> ctypes array of ccqp_block."""
-    rows = [tuple(int(v) for v in r) for r in rows]
-    arr = (Block * len(rows))()
-    for k, (kind, off, dim, poff) in enumerate(rows):
-        arr[k].kind, arr[k].reserved, arr[k].offset, arr[k].dim, arr[k].param_off = kind, 0, off, dim, poff
-    return arr
+    """rows: iterable of (kind, offset, dim, param_off) -> BlockArray (pass `.ptr` to the ABI)."""
+    return BlockArray(rows)
 
 
 def f64_ptr(a):

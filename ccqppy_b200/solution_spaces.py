@@ -29,6 +29,27 @@ def _handle():
     return _proj_handle
 
 
+class _ParamBuf:
+    """Growing parameter array of a block table (chunks are concatenated once at the end)."""
+
+    def __init__(self):
+        self.chunks, self.size = [], 0
+
+    def __len__(self):
+        return self.size
+
+    def extend(self, arr):
+        arr = np.asarray(arr, dtype=np.float64).ravel()
+        self.chunks.append(arr)
+        self.size += arr.size
+
+    def append(self, value):
+        self.extend([float(value)])
+
+    def array(self):
+        return np.concatenate(self.chunks) if self.chunks else np.zeros(0)
+
+
 def _per_element(value, dim, default):
     if value is None:
         return np.full(dim, float(default))
@@ -52,14 +73,14 @@ class ProjOpBase(ABC):
 
     @abstractmethod
     def _blocks(self, offset, params):
-        """Append this operator's parameters to `params` (a list) and return its block rows
+        """Append this operator's parameters to `params` (a _ParamBuf) and return its block rows
         [(kind, offset, dim, param_off), ...]."""
 
     def descriptor(self):
         """Flat block table for the C-ABI: (ctypes ccqp_block array, float64 params array)."""
-        params = []
+        params = _ParamBuf()
         rows = self._blocks(0, params)
-        return _capi.make_blocks(rows), np.asarray(params, dtype=np.float64), rows
+        return _capi.make_blocks(rows), params.array(), rows
 
     # -- GPU evaluation through the unit-test hooks of the ABI --------------------------------
     def _run(self, fn_name, x):
@@ -75,7 +96,7 @@ class ProjOpBase(ABC):
         h = _handle()
         blocks, params, _ = self.descriptor()
         pp, _, _k1 = _capi.f64_ptr(params if params.size else np.zeros(1))
-        _capi.check(h.h, h.lib.ccqp_set_projection(h.h, blocks, len(blocks), pp, params.size))
+        _capi.check(h.h, h.lib.ccqp_set_projection(h.h, blocks.ptr, len(blocks), pp, params.size))
         px, mem, _k2 = _capi.f64_ptr(xin)
         po, _, _k3 = _capi.f64_ptr(out)
         st = getattr(h.lib, fn_name)(h.h, px, po, mem)
@@ -123,7 +144,7 @@ class LowerBoundProjOp(ProjOpBase):
 
     def _blocks(self, offset, params):
         poff = len(params)
-        params.extend(_per_element(self.lower_bound, self.dim, -1.0).tolist())
+        params.extend(_per_element(self.lower_bound, self.dim, -1.0))
         return [(_capi.LOWER, offset, self.dim, poff)]
 
 
@@ -140,7 +161,7 @@ class UpperBoundProjOp(ProjOpBase):
 
     def _blocks(self, offset, params):
         poff = len(params)
-        params.extend(_per_element(self.upper_bound, self.dim, 1.0).tolist())
+        params.extend(_per_element(self.upper_bound, self.dim, 1.0))
         return [(_capi.UPPER, offset, self.dim, poff)]
 
 
@@ -158,8 +179,8 @@ class BoxProjOp(ProjOpBase):
 
     def _blocks(self, offset, params):
         poff = len(params)
-        params.extend(_per_element(self.lower_bound, self.dim, -1.0).tolist())
-        params.extend(_per_element(self.upper_bound, self.dim, 1.0).tolist())
+        params.extend(_per_element(self.lower_bound, self.dim, -1.0))
+        params.extend(_per_element(self.upper_bound, self.dim, 1.0))
         return [(_capi.BOX, offset, self.dim, poff)]
 
 
@@ -226,6 +247,17 @@ class DisjointProjOp(ProjOpBase):
         self.dim = 0
         for op in self.proj_ops:
             self.dim += op.embedded_dimension
+        self._desc = None
+
+    def descriptor(self):
+        # flattening ~1e4 Python operator objects costs tens of ms; the tuple of operators is fixed
+        # at construction, so the table is built once (call invalidate() after mutating a member)
+        if self._desc is None:
+            self._desc = super().descriptor()
+        return self._desc
+
+    def invalidate(self):
+        self._desc = None
 
     @property
     def name(self):

@@ -148,7 +148,7 @@ class CCQPSolverBase(ABC):
         _capi.check(h.h, lib.ccqp_set_matrix(h.h, pa, num_unknowns, lda, 0, num_unknowns, mem_a))
         blocks, params, _rows = convex_proj_op.descriptor()
         pp, _, _kp = _capi.f64_ptr(params if params.size else np.zeros(1))
-        _capi.check(h.h, lib.ccqp_set_projection(h.h, blocks, len(blocks), pp, params.size))
+        _capi.check(h.h, lib.ccqp_set_projection(h.h, blocks.ptr, len(blocks), pp, params.size))
 
         rng_state = None
         uni = None
