@@ -22,7 +22,7 @@ ERR_RANGE = 8
 EXPORTS = ["ccqp_abi_version", "ccqp_status_string", "ccqp_last_error", "ccqp_create", "ccqp_destroy",
            "ccqp_set_stream", "ccqp_get_info", "ccqp_set_matrix", "ccqp_set_projection", "ccqp_solve",
            "ccqp_solve_batched", "ccqp_gemv", "ccqp_gemv_timed", "ccqp_project", "ccqp_normal", "ccqp_comm_export",
-           "ccqp_comm_attach", "ccqp_comm_detach"]
+           "ccqp_comm_attach", "ccqp_comm_prepare", "ccqp_comm_detach"]
 
 
 class Block(C.Structure):
@@ -82,6 +82,7 @@ def load():
     lib.ccqp_normal.argtypes = [vp, dp, dp, i32]
     lib.ccqp_comm_export.argtypes = [vp, i32, i32, i64, vp]
     lib.ccqp_comm_attach.argtypes = [vp, vp]
+    lib.ccqp_comm_prepare.argtypes = [vp]
     lib.ccqp_comm_detach.argtypes = [vp]
     for name in EXPORTS:
         fn = getattr(lib, name)

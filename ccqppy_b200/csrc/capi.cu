@@ -53,6 +53,10 @@ struct ccqp_handle {
     void* out_host = nullptr;   // pinned
     long long npad = 0;
     long long launches = 0;
+    // row-sharded multi-GPU solves: peers' symmetric buffers mapped through CUDA IPC
+    int world = 1, rank = 0;
+    char* peer_base[kMaxWorld] = {nullptr};
+    bool comm_ready = false;
 };
 
 namespace {
@@ -88,15 +92,21 @@ ccqp_status copy_out(ccqp_handle* h, double* dst, const double* src, long long c
 // slots of the work buffer (each npad doubles)
 enum { W_B = 0, W_X0, W_XOUT, W_HIN, W_HOUT, W_VEC0, W_COUNT = W_VEC0 + kNumVec };
 
+// The work buffer has the layout of the multi-GPU symmetric buffer (common.cuh kSym*Off): flags,
+// scalar exchange slots, then the work vectors.  Single GPU: a private allocation.  Sharded: the
+// allocation exported to the peers, fixed at ccqp_comm_export() time.
+size_t work_bytes(long long npad) { return kSymVecOff + (size_t)W_COUNT * npad * 8; }
+
 ccqp_status ensure_work(ccqp_handle* h) {
     const long long npad = round_up(h->n, 64) + 64;
     if (npad != h->npad || !h->work.p) {
-        CU(h, h->work.ensure((size_t)W_COUNT * npad * 8));
+        if (h->world > 1) { h->last_error = "problem size differs from the one given to ccqp_comm_export"; return CCQP_ERR_COMM; }
+        CU(h, h->work.ensure(work_bytes(npad)));
         h->npad = npad;
     }
     CU(h, h->partials.ensure((size_t)2 * h->sm_count * kMaxRed * 8));
     CU(h, h->andparts.ensure((size_t)2 * h->sm_count * 8));
-    CU(h, h->flags.ensure(64));
+    CU(h, h->flags.ensure(256));
     CU(h, h->out_dev.ensure(sizeof(DenseOut)));
     if (!h->out_host) CU(h, cudaMallocHost(&h->out_host, 4096));
     return CCQP_OK;
@@ -128,7 +138,7 @@ Tiling choose_tiling(const ccqp_handle* h) {
 
 void fill_ctx(ccqp_handle* h, DenseCtx& c, const Tiling& t) {
     std::memset(&c, 0, sizeof(c));
-    double* w = h->work.as<double>();
+    double* w = reinterpret_cast<double*>(h->work.as<char>() + kSymVecOff);
     c.A = h->dA; c.lda = h->lda; c.n = (int)h->n; c.row0 = (int)h->row0; c.nrows = (int)h->nrows;
     c.aligned = ((reinterpret_cast<uintptr_t>(h->dA) & 31) == 0 && (h->lda % 4) == 0) ? 1 : 0;
     c.b = w + W_B * h->npad; c.x0 = w + W_X0 * h->npad; c.x_out = w + W_XOUT * h->npad;
@@ -147,6 +157,11 @@ void fill_ctx(ccqp_handle* h, DenseCtx& c, const Tiling& t) {
     c.andparts = h->andparts.as<unsigned long long>();
     c.bar_counter = h->flags.as<unsigned>();
     c.abort_flag = h->flags.as<unsigned>() + 8;
+    c.x.world = h->world; c.x.rank = h->rank;
+    for (int s = 0; s < kMaxWorld; ++s) c.x.base[s] = (s < h->world) ? h->peer_base[s] : nullptr;
+    if (h->world == 1) c.x.base[0] = h->work.as<char>();
+    c.x.local_arrive = h->flags.as<unsigned>() + 16;
+    c.x.local_go = h->flags.as<unsigned>() + 24;
     c.out = h->out_dev.as<DenseOut>();
     c.CW = t.CW; c.SW = t.SW; c.np = t.np; c.nseg = t.nseg; c.rows_max = t.rows_max;
     c.evict_first = ((double)h->nrows * (double)h->n * 8.0 > 96.0 * 1024 * 1024) ? 1 : 0;
@@ -160,7 +175,7 @@ ccqp_status launch_dense(ccqp_handle* h, DenseCtx& c, const Tiling& t, bool coop
         CU(h, cudaFuncSetAttribute(dense_kernel<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
         configured = 220 * 1024;
     }
-    if (cooperative) CU(h, cudaMemsetAsync(h->flags.p, 0, 64, h->stream));   // barrier counter
+    if (cooperative) CU(h, cudaMemsetAsync(h->flags.p, 0, 256, h->stream));   // barrier counters
     void* args[] = {&c};
     if (cooperative)
         CU(h, cudaLaunchCooperativeKernel((const void*)dense_kernel<OP>, dim3(t.grid), dim3(kDenseThreads), args, t.smem, h->stream));
@@ -233,6 +248,7 @@ ccqp_status ccqp_destroy(ccqp_handle* h) {
     if (!h) return CCQP_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    if (h->world > 1) ccqp_comm_detach(h);
     DevBuf* bufs[] = {&h->a_own, &h->lo, &h->hi, &h->ekind, &h->bkind, &h->boff, &h->bdim, &h->bpar, &h->small_ids,
                       &h->big_ids, &h->work, &h->partials, &h->andparts, &h->flags, &h->out_dev, &h->uniforms,
                       &h->batched_ws};
@@ -355,14 +371,18 @@ ccqp_status ccqp_solve(ccqp_handle* h, int solver, const ccqp_params* params, co
         return CCQP_ERR_INVALID_ARG;
     if (!h->dA || !h->have_proj) return CCQP_ERR_NOT_READY;
     if (h->proj_n != h->n) return CCQP_ERR_INVALID_ARG;
-    if (h->row0 != 0 || h->nrows != h->n) return CCQP_ERR_UNSUPPORTED;   // sharded solves need ccqp_comm_attach
+    const bool sharded = h->world > 1;
+    if (!sharded && (h->row0 != 0 || h->nrows != h->n)) return CCQP_ERR_UNSUPPORTED;   // a shard needs ccqp_comm_attach
+    if (sharded && !h->comm_ready) return CCQP_ERR_NOT_READY;
     CU(h, cudaSetDevice(h->device));
     ccqp_status st = ensure_work(h);
     if (st != CCQP_OK) return st;
     const long long n = h->n, npad = h->npad;
-    double* w = h->work.as<double>();
-    // zero b/x0 slots (tails must be zero), then fill
-    CU(h, cudaMemsetAsync(w, 0, (size_t)W_COUNT * npad * 8, h->stream));
+    double* w = reinterpret_cast<double*>(h->work.as<char>() + kSymVecOff);
+    // zero everything (vector tails must be zero), then fill.  Sharded: ccqp_comm_prepare() did it
+    // before the host-side barrier, because peers write into this buffer as soon as they start.
+    if (!sharded) CU(h, cudaMemsetAsync(h->work.p, 0, work_bytes(npad), h->stream));
+    else if (!x0) CU(h, cudaMemsetAsync(w + W_X0 * npad, 0, (size_t)npad * 8, h->stream));
     if ((st = copy_in(h, w + W_B * npad, b, n, memtype)) != CCQP_OK) return st;
     if (x0 && (st = copy_in(h, w + W_X0 * npad, x0, n, memtype)) != CCQP_OK) return st;
     const Tiling t = choose_tiling(h);
@@ -420,8 +440,9 @@ static ccqp_status run_hook(ccqp_handle* h, int op, const double* in, double* ou
     }
     ccqp_status st = ensure_work(h);
     if (st != CCQP_OK) return st;
+    if (h->world > 1) return CCQP_ERR_UNSUPPORTED;   // hooks are single-GPU
     const long long npad = h->npad;
-    double* w = h->work.as<double>();
+    double* w = reinterpret_cast<double*>(h->work.as<char>() + kSymVecOff);
     CU(h, cudaMemsetAsync(w + W_HIN * npad, 0, (size_t)2 * npad * 8, h->stream));
     if ((st = copy_in(h, w + W_HIN * npad, in, n_in, memtype)) != CCQP_OK) return st;
     Tiling t;
@@ -491,8 +512,70 @@ ccqp_status ccqp_solve_batched(ccqp_handle* h, int solver, const ccqp_params* pa
     return st;
 }
 
-ccqp_status ccqp_comm_export(ccqp_handle*, int, int, int64_t, void*) { return CCQP_ERR_UNSUPPORTED; }
-ccqp_status ccqp_comm_attach(ccqp_handle*, const void*) { return CCQP_ERR_UNSUPPORTED; }
-ccqp_status ccqp_comm_detach(ccqp_handle*) { return CCQP_ERR_UNSUPPORTED; }
+struct CommDesc {                 // CCQP_COMM_DESC_BYTES = 128
+    cudaIpcMemHandle_t handle;    // 64 bytes
+    unsigned long long bytes;
+    long long n;
+    int device, rank, world, abi;
+    char pad[128 - 64 - 8 - 8 - 16];
+};
+static_assert(sizeof(CommDesc) == CCQP_COMM_DESC_BYTES, "descriptor size");
+
+ccqp_status ccqp_comm_export(ccqp_handle* h, int rank, int world, int64_t n, void* desc) {
+    if (!h || !desc || world < 2 || world > kMaxWorld || rank < 0 || rank >= world || n <= 0) return CCQP_ERR_INVALID_ARG;
+    CU(h, cudaSetDevice(h->device));
+    if (h->comm_ready) ccqp_comm_detach(h);
+    const long long npad = round_up(n, 64) + 64;
+    h->work.release();                                    // a fresh allocation: the IPC handle names its base
+    CU(h, h->work.ensure(work_bytes(npad)));
+    h->npad = npad; h->n = n;
+    CU(h, cudaMemset(h->work.p, 0, work_bytes(npad)));
+    CommDesc d;
+    std::memset(&d, 0, sizeof(d));
+    CU(h, cudaIpcGetMemHandle(&d.handle, h->work.p));
+    d.bytes = work_bytes(npad); d.n = n; d.device = h->device; d.rank = rank; d.world = world; d.abi = CCQP_ABI_VERSION;
+    std::memcpy(desc, &d, sizeof(d));
+    h->world = world; h->rank = rank; h->comm_ready = false;
+    return CCQP_OK;
+}
+
+ccqp_status ccqp_comm_attach(ccqp_handle* h, const void* all_descs) {
+    if (!h || !all_descs || h->world < 2) return CCQP_ERR_INVALID_ARG;
+    CU(h, cudaSetDevice(h->device));
+    const CommDesc* d = static_cast<const CommDesc*>(all_descs);
+    for (int s = 0; s < h->world; ++s) {
+        if (d[s].rank != s || d[s].world != h->world || d[s].n != h->n || d[s].abi != CCQP_ABI_VERSION ||
+            d[s].bytes != work_bytes(h->npad)) { h->last_error = "inconsistent exchange descriptors"; return CCQP_ERR_COMM; }
+        if (s == h->rank) { h->peer_base[s] = h->work.as<char>(); continue; }
+        void* p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, d[s].handle, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            h->last_error = std::string("cudaIpcOpenMemHandle(rank ") + std::to_string(s) + "): " + cudaGetErrorString(e);
+            return CCQP_ERR_COMM;
+        }
+        h->peer_base[s] = static_cast<char*>(p);
+    }
+    h->comm_ready = true;
+    return CCQP_OK;
+}
+
+ccqp_status ccqp_comm_prepare(ccqp_handle* h) {
+    if (!h || h->world < 2 || !h->comm_ready) return CCQP_ERR_NOT_READY;
+    CU(h, cudaSetDevice(h->device));
+    CU(h, cudaMemsetAsync(h->work.p, 0, work_bytes(h->npad), h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return CCQP_OK;
+}
+
+ccqp_status ccqp_comm_detach(ccqp_handle* h) {
+    if (!h) return CCQP_ERR_INVALID_ARG;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    for (int s = 0; s < h->world; ++s)
+        if (s != h->rank && h->peer_base[s]) cudaIpcCloseMemHandle(h->peer_base[s]);
+    for (int s = 0; s < kMaxWorld; ++s) h->peer_base[s] = nullptr;
+    h->world = 1; h->rank = 0; h->comm_ready = false;
+    return CCQP_OK;
+}
 
 }  // extern "C"

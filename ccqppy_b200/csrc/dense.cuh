@@ -79,6 +79,8 @@ struct DenseCtx {
     // test hooks
     const double* hook_in;
     double* hook_out;
+    // row-sharded multi-GPU solves (world == 1: unused)
+    XComm x;
 };
 
 // shared memory carve-up (dynamic)
@@ -102,6 +104,7 @@ __host__ __device__ inline size_t dense_smem_bytes(int CW, int rows_max, int nse
 
 struct Kst {                // per-thread kernel state
     GridSync gs;
+    XSync xs;
     DenseSmem sm;
     int gtid, gstride;
     int r0, r1;             // rows of this CTA (global indices)
@@ -113,6 +116,24 @@ struct Kst {                // per-thread kernel state
 // ------------------------------------------------------------------------------------------
 // reductions across the grid (the barrier also orders all prior global writes)
 // ------------------------------------------------------------------------------------------
+// Barrier between phases.  Single GPU: grid barrier.  Sharded: every rank's grid + all ranks.
+__device__ __forceinline__ void barrier_only(Kst& k, const DenseCtx& c) {
+    if (c.x.world > 1) xgpu_barrier(c.x, k.xs, c.abort_flag);
+    else grid_barrier(k.gs);
+}
+
+// store into a vector that a later mat-vec reads in full: the owning rank also writes the entry
+// into every peer's copy of the vector (same offset in the peer's symmetric buffer, over NVLink)
+__device__ __forceinline__ void pub_store(const DenseCtx& c, double* vec, int i, double v) {
+    vec[i] = v;
+    if (c.x.world > 1) {
+        const size_t off = reinterpret_cast<char*>(vec + i) - c.x.base[c.x.rank];
+#pragma unroll 1
+        for (int s = 0; s < c.x.world; ++s)
+            if (s != c.x.rank) *reinterpret_cast<double*>(c.x.base[s] + off) = v;
+    }
+}
+
 template <int K>
 __device__ __forceinline__ void reduce_sync(Kst& k, const DenseCtx& c, double (&a)[K]) {
     static_assert(K <= kMaxRed, "too many reduction slots");
@@ -135,13 +156,29 @@ __device__ __forceinline__ void reduce_sync(Kst& k, const DenseCtx& c, double (&
         }
     }
     __syncthreads();
+    if (c.x.world > 1) {
+        // rank-local sums -> every peer's xpart[buf][rank][:], then all ranks add the world's
+        // contributions in rank order, so every rank holds bit-identical scalars
+        if (blockIdx.x == 0 && threadIdx.x < K) {
+            const double v = k.sm.scratch[threadIdx.x];
+            const size_t off = kSymXpartOff + (((size_t)k.redbuf * kMaxWorld + c.x.rank) * kMaxRed + threadIdx.x) * 8;
+            for (int s = 0; s < c.x.world; ++s) *reinterpret_cast<double*>(c.x.base[s] + off) = v;
+        }
+        xgpu_barrier(c.x, k.xs, c.abort_flag);
+        if (threadIdx.x < K) {
+            const double* xp = reinterpret_cast<const double*>(c.x.base[c.x.rank] + kSymXpartOff) +
+                               (size_t)k.redbuf * kMaxWorld * kMaxRed + threadIdx.x;
+            double s = 0.0;
+            for (int r = 0; r < c.x.world; ++r) s += ld_cg(xp + (size_t)r * kMaxRed);
+            k.sm.scratch[threadIdx.x] = s;
+        }
+        __syncthreads();
+    }
 #pragma unroll
     for (int j = 0; j < K; ++j) a[j] = k.sm.scratch[j];
     __syncthreads();
     k.redbuf ^= 1;
 }
-
-__device__ __forceinline__ void barrier_only(Kst& k) { grid_barrier(k.gs); }
 
 // bitwise AND of a 64-bit mask over the grid
 __device__ __forceinline__ unsigned long long and_sync(Kst& k, const DenseCtx& c, unsigned long long m) {
@@ -168,6 +205,26 @@ __device__ __forceinline__ unsigned long long and_sync(Kst& k, const DenseCtx& c
         if (lane == 0) k.sm.ascratch[0] = t;
     }
     __syncthreads();
+    if (c.x.world > 1) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            const unsigned long long v = k.sm.ascratch[0];
+            const size_t off = kSymApartOff + ((size_t)k.redbuf * kMaxWorld + c.x.rank) * 8;
+            for (int s = 0; s < c.x.world; ++s) *reinterpret_cast<unsigned long long*>(c.x.base[s] + off) = v;
+        }
+        xgpu_barrier(c.x, k.xs, c.abort_flag);
+        if (threadIdx.x == 0) {
+            const unsigned long long* ap = reinterpret_cast<const unsigned long long*>(c.x.base[c.x.rank] + kSymApartOff) +
+                                           (size_t)k.redbuf * kMaxWorld;
+            unsigned long long t = ~0ull;
+            for (int r = 0; r < c.x.world; ++r) {
+                unsigned long long v;
+                asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(v) : "l"(ap + r) : "memory");
+                t &= v;
+            }
+            k.sm.ascratch[0] = t;
+        }
+        __syncthreads();
+    }
     const unsigned long long r = k.sm.ascratch[0];
     __syncthreads();
     k.redbuf ^= 1;
@@ -303,7 +360,7 @@ __device__ __forceinline__ double residual_partial(Kst& k, const DenseCtx& c, do
 }
 
 __device__ __forceinline__ void finish(Kst& k, const DenseCtx& c, const double* xsol, double res, int status) {
-    CCQP_ELEMS(i) c.x_out[i] = ld_cg(xsol + i);
+    CCQP_ELEMS(i) pub_store(c, c.x_out, i, ld_cg(xsol + i));   // every rank returns the full solution
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         DenseOut o;
         o.residual = res;
@@ -312,6 +369,7 @@ __device__ __forceinline__ void finish(Kst& k, const DenseCtx& c, const double* 
         o.status = status;
         *c.out = o;
     }
+    if (c.x.world > 1) xgpu_barrier(c.x, k.xs, c.abort_flag);   // peers' slices of x_out have landed
 }
 
 __device__ __forceinline__ bool hit_max(const Kst& k, const DenseCtx& c) { return (double)k.mv >= c.max_mv; }
@@ -325,11 +383,11 @@ __device__ void solve_pgd_family(Kst& k, const DenseCtx& c) {
     double *xmin = c.vec[4], *gmin = c.vec[5];
     const double cs = 1.0 / (3 * (double)c.n * kGd);
     const double* b = c.b;
-    CCQP_ELEMS(i) { const double v = c.x0[i]; x[i] = v; xm[i] = v; if (MODE == OP_BBPGDF) { xmin[i] = v; gmin[i] = v; } }
-    barrier_only(k);
-    gemv_phase(k, c, xm, [&](int r, double s) { gm[r] = s + b[r]; });
+    CCQP_ELEMS(i) { const double v = c.x0[i]; x[i] = v; pub_store(c, xm, i, v); if (MODE == OP_BBPGDF) { xmin[i] = v; gmin[i] = v; } }
+    barrier_only(k, c);
+    gemv_phase(k, c, xm, [&](int r, double s) { pub_store(c, gm, r, s + b[r]); });   // gm feeds A gm below
     k.mv = 1;
-    barrier_only(k);
+    barrier_only(k, c);
     double a1[1] = {residual_partial(k, c, cs, [&](int i) { return ld_cg(xm + i); }, [&](int i) { return ld_cg(gm + i); })};
     reduce_sync<1>(k, c, a1);
     double res = sqrt(a1[0]);
@@ -346,11 +404,11 @@ __device__ void solve_pgd_family(Kst& k, const DenseCtx& c) {
         for (;;) {
             project_pass(c.T, k.gtid, k.gstride, k.sm.scratch,
                          [&](int i) { return ld_cg(xm + i) - step * ld_cg(gm + i); },
-                         [&](int i, double, double p) { x[i] = p; });
-            barrier_only(k);
+                         [&](int i, double, double p) { pub_store(c, x, i, p); });
+            barrier_only(k, c);
             gemv_phase(k, c, x, [&](int r, double s) { g[r] = s + b[r]; });
             k.mv += 1;
-            barrier_only(k);
+            barrier_only(k, c);
             xsol = x;
             if (hit_max(k, c)) break;
             double a3[3] = {0.0, 0.0, 0.0};
@@ -376,11 +434,11 @@ __device__ void solve_pgd_family(Kst& k, const DenseCtx& c) {
                     CCQP_ELEMS(i) { xmin[i] = ld_cg(x + i); gmin[i] = ld_cg(g + i); }
                 }
                 if (step < 10 * kEps) {   // stagnation: x replaced (g is not), BB sums redone
-                    barrier_only(k);
+                    barrier_only(k, c);
                     project_pass(c.T, k.gtid, k.gstride, k.sm.scratch,
                                  [&](int i) { return ld_cg(xmin + i) - kGd * ld_cg(gmin + i); },
-                                 [&](int i, double, double p) { x[i] = p; });
-                    barrier_only(k);
+                                 [&](int i, double, double p) { pub_store(c, x, i, p); });
+                    barrier_only(k, c);
                     double a2[2] = {0.0, 0.0};
                     CCQP_ELEMS(i) {
                         const double s = ld_cg(x + i) - ld_cg(xm + i), y = ld_cg(g + i) - ld_cg(gm + i);
@@ -396,7 +454,7 @@ __device__ void solve_pgd_family(Kst& k, const DenseCtx& c) {
             swap_ptr(g, gm);
         }
     }
-    barrier_only(k);
+    barrier_only(k, c);
     finish(k, c, xsol, res, 0);
 }
 
@@ -406,12 +464,12 @@ __device__ void solve_pgd_family(Kst& k, const DenseCtx& c) {
 __device__ void solve_spg(Kst& k, const DenseCtx& c) {
     double *x = c.vec[0], *g = c.vec[1], *d = c.vec[2], *Ad = c.vec[3];
     const double* b = c.b;
-    CCQP_ELEMS(i) x[i] = c.x0[i];
-    barrier_only(k);
+    CCQP_ELEMS(i) pub_store(c, x, i, c.x0[i]);
+    barrier_only(k, c);
     double a2[2] = {0.0, 0.0};
     gemv_phase(k, c, x, [&](int r, double s) {
         const double gr = s + b[r];
-        g[r] = gr;
+        pub_store(c, g, r, gr);                  // g feeds A g below
         a2[0] = fma(gr, ld_cg(x + r), a2[0]);   // f0 = g.x (:923, kept as written)
         a2[1] = fma(gr, gr, a2[1]);
     });
@@ -442,7 +500,8 @@ __device__ void solve_spg(Kst& k, const DenseCtx& c) {
                          const double xi = fma(bk, ld_cg(d + i), ld_cg(x + i));
                          const double gi = fma(bk, ld_cg(Ad + i), ld_cg(g + i));
                          const double di = p - xi;
-                         x[i] = xi; g[i] = gi; d[i] = di;
+                         x[i] = xi; g[i] = gi;
+                         pub_store(c, d, i, di);
                          s2[0] = fma(di, di, s2[0]);
                          s2[1] = fma(di, gi, s2[1]);
                      });
@@ -474,7 +533,7 @@ __device__ void solve_spg(Kst& k, const DenseCtx& c) {
         alpha = dd / dAd;
         k.iters += 1;
     }
-    barrier_only(k);
+    barrier_only(k, c);
     finish(k, c, x, sqrt(dd_rep), status);
 }
 
@@ -490,10 +549,11 @@ __device__ void solve_apgd(Kst& k, const DenseCtx& c) {
     double a1[1] = {0.0};
     CCQP_ELEMS(i) {
         const double v = c.x0[i];
-        x[i] = v; y[i] = v; xp[i] = v;
+        x[i] = v; xp[i] = v;
+        pub_store(c, y, i, v);
         if (AR) xhat[i] = 1.0;
         const double dv = v - 1.0;
-        v0[i] = dv;
+        pub_store(c, v0, i, dv);
         a1[0] = fma(dv, dv, a1[0]);
     }
     reduce_sync<1>(k, c, a1);
@@ -519,8 +579,8 @@ __device__ void solve_apgd(Kst& k, const DenseCtx& c) {
         const double rt1 = r12[0] * 0.5, rt2 = r12[1];
         project_pass(c.T, k.gtid, k.gstride, k.sm.scratch,
                      [&](int i) { return ld_cg(y + i) - t * ld_cg(g + i); },
-                     [&](int i, double, double p) { xp[i] = p; });
-        barrier_only(k);
+                     [&](int i, double, double p) { pub_store(c, xp, i, p); });
+        barrier_only(k, c);
         for (;;) {   // Lipschitz backtracking :288-310
             double q[4] = {0.0, 0.0, 0.0, 0.0};
             gemv_phase(k, c, xp, [&](int r, double s) {
@@ -540,8 +600,8 @@ __device__ void solve_apgd(Kst& k, const DenseCtx& c) {
             t = 1.0 / L;
             project_pass(c.T, k.gtid, k.gstride, k.sm.scratch,
                          [&](int i) { return ld_cg(y + i) - t * ld_cg(g + i); },
-                         [&](int i, double, double p) { xp[i] = p; });
-            barrier_only(k);
+                         [&](int i, double, double p) { pub_store(c, xp, i, p); });
+            barrier_only(k, c);
         }
         double theta_n = 0.5 * (-theta * theta + theta * sqrt(4 + theta * theta));
         const double beta = theta * (1 - theta) / (theta * theta + theta_n);
@@ -553,7 +613,7 @@ __device__ void solve_apgd(Kst& k, const DenseCtx& c) {
                          const double dr = cs * (xpi - p);
                          r2[0] = fma(dr, dr, r2[0]);
                          if (AR) r2[1] = fma(ld_cg(g + i), xpi - xi, r2[1]);
-                         yn[i] = (1 + beta) * xpi - beta * xi;
+                         pub_store(c, yn, i, (1 + beta) * xpi - beta * xi);
                      });
         reduce_sync<2>(k, c, r2);
         res = sqrt(r2[0]);
@@ -564,9 +624,9 @@ __device__ void solve_apgd(Kst& k, const DenseCtx& c) {
         }
         if (res < c.tol) break;
         if (AR && r2[1] > 0) {   // :510-512
-            CCQP_ELEMS(i) yn[i] = ld_cg(xp + i);
+            CCQP_ELEMS(i) pub_store(c, yn, i, ld_cg(xp + i));
             theta_n = 1;
-            barrier_only(k);
+            barrier_only(k, c);
         }
         L *= 0.9;
         t = 1.0 / L;
@@ -574,7 +634,7 @@ __device__ void solve_apgd(Kst& k, const DenseCtx& c) {
         swap_ptr(x, xp);   // afterwards xp names the previous x (what :336 returns on the mv limit)
         theta = theta_n;
     }
-    barrier_only(k);
+    barrier_only(k, c);
     finish(k, c, AR ? xhat : xp, res, 0);
 }
 
@@ -617,11 +677,11 @@ __device__ void solve_mprgp(Kst& k, const DenseCtx& c) {
     const double cs = 1.0 / (3 * (double)c.n * kGd);
     int status = 0;
     project_pass(c.T, k.gtid, k.gstride, k.sm.scratch, [&](int i) { return c.x0[i]; },
-                 [&](int i, double, double pr) { xk[i] = pr; xn[i] = pr; });
-    barrier_only(k);
-    gemv_phase(k, c, xk, [&](int r, double s) { const double v = s + b[r]; gk[r] = v; gn[r] = v; });
+                 [&](int i, double, double pr) { pub_store(c, xk, i, pr); xn[i] = pr; });
+    barrier_only(k, c);
+    gemv_phase(k, c, xk, [&](int r, double s) { const double v = s + b[r]; pub_store(c, gk, r, v); gn[r] = v; });
     k.mv = 1;
-    barrier_only(k);
+    barrier_only(k, c);
     double a1[1] = {residual_partial(k, c, cs, [&](int i) { return ld_cg(xk + i); }, [&](int i) { return ld_cg(gk + i); })};
     reduce_sync<1>(k, c, a1);
     double res = sqrt(a1[0]);
@@ -633,12 +693,12 @@ __device__ void solve_mprgp(Kst& k, const DenseCtx& c) {
         double abb = a2[1] / a2[0];
         bool abb_lazy = false;                       // true: abb = BB(xk - xn) still to be evaluated
         project_pass(c.T, k.gtid, k.gstride, k.sm.scratch, [&](int i) { return ld_cg(xk + i); },
-                     [&](int i, double t, double pr) { p[i] = is_close(t, pr) ? ld_cg(gk + i) : 0.0; });
-        barrier_only(k);
+                     [&](int i, double t, double pr) { pub_store(c, p, i, is_close(t, pr) ? ld_cg(gk + i) : 0.0); });
+        barrier_only(k, c);
         for (;;) {
             gemv_phase(k, c, xk, [&](int r, double s) { gk[r] = s + b[r]; });
             k.mv += 1;
-            barrier_only(k);
+            barrier_only(k, c);
             if (hit_max(k, c)) break;
             // delta = isclose(xk, P(xk)); psi = delta*gk   (:1093-1094)
             double q3[3] = {0.0, 0.0, 0.0};          // psi.psi, psi.p, #(!delta)
@@ -658,7 +718,7 @@ __device__ void solve_mprgp(Kst& k, const DenseCtx& c) {
                 // rare: some entries of xk are not (close to) feasible; the chopped gradient
                 // needs normal_vector(xk) and the GLOBAL n.g (:1095-1097)
                 normal_pass(c.T, k.gtid, k.gstride, k.sm.scratch, [&](int i) { return ld_cg(xk + i); }, nv);
-                barrier_only(k);
+                barrier_only(k, c);
                 double s1[1] = {0.0};
                 CCQP_ELEMS(i) s1[0] = fma(ld_cg(nv + i), ld_cg(gk + i), s1[0]);
                 reduce_sync<1>(k, c, s1);
@@ -693,11 +753,11 @@ __device__ void solve_mprgp(Kst& k, const DenseCtx& c) {
                                  [&](int i, double yv, double pr) {
                                      const double api = ld_cg(Ap + i);
                                      const double gni = ld_cg(gk + i) - acg * api;
-                                     xn[i] = yv;
+                                     pub_store(c, xn, i, yv);
                                      gn[i] = gni;
                                      const double psy = is_close(yv, pr) ? gni : 0.0;
                                      const double bet = psy * api / pAp;          // elementwise "beta" (:1134)
-                                     p[i] = psy - bet * ld_cg(p + i);
+                                     pub_store(c, p, i, psy - bet * ld_cg(p + i));
                                  });
                     abb_lazy = true;   // same element->thread map as the residual pass: no barrier
                 } else {
@@ -718,21 +778,21 @@ __device__ void solve_mprgp(Kst& k, const DenseCtx& c) {
                                      const double gh = ld_cg(gk + i) - af * ld_cg(Ap + i);
                                      return xh - a * gh;
                                  },
-                                 [&](int i, double, double pr) { xn[i] = pr; });
-                    barrier_only(k);
+                                 [&](int i, double, double pr) { pub_store(c, xn, i, pr); });
+                    barrier_only(k, c);
                     gemv_phase(k, c, xn, [&](int r, double s) { gn[r] = s + b[r]; });
                     k.mv += 1;
-                    barrier_only(k);
+                    barrier_only(k, c);
                     if (hit_max(k, c)) break;
                     project_pass(c.T, k.gtid, k.gstride, k.sm.scratch, [&](int i) { return ld_cg(xn + i); },
-                                 [&](int i, double t, double pr) { p[i] = is_close(t, pr) ? ld_cg(gn + i) : 0.0; });
+                                 [&](int i, double t, double pr) { pub_store(c, p, i, is_close(t, pr) ? ld_cg(gn + i) : 0.0); });
                     abb_lazy = true;
                 }
             } else {
                 // proportioning step :1164-1182
                 if (abb_lazy) {   // alpha_bb of the previous iteration, evaluated only when needed
                     double s1[1] = {0.0};
-                    CCQP_ELEMS(i) { const double dv = ld_cg(xk + i) - ld_cg(xn + i); w[i] = dv; s1[0] = fma(dv, dv, s1[0]); }
+                    CCQP_ELEMS(i) { const double dv = ld_cg(xk + i) - ld_cg(xn + i); pub_store(c, w, i, dv); s1[0] = fma(dv, dv, s1[0]); }
                     reduce_sync<1>(k, c, s1);
                     double s2[1] = {0.0};
                     gemv_phase(k, c, w, [&](int r, double s) { s2[0] = fma(ld_cg(w + r), s, s2[0]); });
@@ -741,13 +801,13 @@ __device__ void solve_mprgp(Kst& k, const DenseCtx& c) {
                 }
                 project_pass(c.T, k.gtid, k.gstride, k.sm.scratch,
                              [&](int i) { return ld_cg(xk + i) - abb * ld_cg(gk + i); },
-                             [&](int i, double, double pr) { xn[i] = pr; });
+                             [&](int i, double, double pr) { pub_store(c, xn, i, pr); });
                 abb_lazy = true;
                 k.mv += 1;            // gk = A xk + b is re-evaluated by the reference (:1174); same value
-                barrier_only(k);
+                barrier_only(k, c);
                 if (hit_max(k, c)) break;
                 project_pass(c.T, k.gtid, k.gstride, k.sm.scratch, [&](int i) { return ld_cg(xn + i); },
-                             [&](int i, double t, double pr) { p[i] = is_close(t, pr) ? ld_cg(gn + i) : 0.0; });   // stale gn (:1181)
+                             [&](int i, double t, double pr) { pub_store(c, p, i, is_close(t, pr) ? ld_cg(gn + i) : 0.0); });   // stale gn (:1181)
             }
             double r1[1] = {residual_partial(k, c, cs, [&](int i) { return ld_cg(xn + i); }, [&](int i) { return ld_cg(gn + i); })};
             reduce_sync<1>(k, c, r1);
@@ -758,7 +818,7 @@ __device__ void solve_mprgp(Kst& k, const DenseCtx& c) {
             swap_ptr(gk, gn);
         }
     }
-    barrier_only(k);
+    barrier_only(k, c);
     finish(k, c, xn, res, status);
 }
 
@@ -781,6 +841,8 @@ __global__ void __launch_bounds__(kDenseThreads, 1) dense_kernel(const DenseCtx 
     k.gs.counter = c.bar_counter;
     k.gs.abort = c.abort_flag;
     k.gs.target = 0;
+    k.xs.epoch = 0;
+    k.xs.arrive_target = 0;
     k.gtid = blockIdx.x * kDenseThreads + threadIdx.x;
     k.gstride = gridDim.x * kDenseThreads;
     k.r0 = c.row0 + (int)(((long long)c.nrows * blockIdx.x) / gridDim.x);

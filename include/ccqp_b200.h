@@ -170,14 +170,22 @@ ccqp_status ccqp_project(ccqp_handle* h, const double* x, double* out, int memty
 /* out = normal_vector(x): solution_spaces.py:92,146,222,306,389,459,512. */
 ccqp_status ccqp_normal(ccqp_handle* h, const double* x, double* out, int memtype);
 
-/* ---- multi-GPU (row-sharded dense solves, one process per GPU) -------------------------------- */
-/* Each rank exports an opaque descriptor of its exchange buffer, the host side all-gathers the
- * descriptors (torch.distributed), and every rank attaches the peers'.  After that ccqp_solve()
- * exchanges vector slices and scalar partials inside the solver kernel through NVLink peer
- * memory.  desc must hold CCQP_COMM_DESC_BYTES bytes. */
+/* ---- multi-GPU (row-sharded dense solves, one process per GPU) --------------------------------
+ * Nothing in the reference corresponds to this (it is single-process NumPy).  A is row-sharded:
+ * every rank calls ccqp_set_matrix() with its rows [row_begin, row_begin+n_rows) (boundaries on
+ * projection-block boundaries) and the FULL projection table.  Setup, once per problem size:
+ *   1. ccqp_comm_export(): allocate this rank's exchange buffer, get an opaque descriptor (CUDA IPC)
+ *   2. the host all-gathers the descriptors (torch.distributed / MPI / files: the ABI does not care)
+ *   3. ccqp_comm_attach(): map every peer's buffer over NVLink
+ * Per solve: ccqp_comm_prepare() (clears the buffer), a HOST barrier across ranks, then ccqp_solve()
+ * on every rank with the same arguments.  Inside the solver kernel each rank writes its slice of
+ * every mat-vec input vector and its scalar partial sums straight into the peers' buffers and the
+ * ranks synchronise through flags in peer memory: no collective launches inside the loop.  Every
+ * rank returns the full solution and identical result fields. */
 #define CCQP_COMM_DESC_BYTES 128
 ccqp_status ccqp_comm_export(ccqp_handle* h, int rank, int world, int64_t n, void* desc);
-ccqp_status ccqp_comm_attach(ccqp_handle* h, const void* all_descs /* world * DESC_BYTES */);
+ccqp_status ccqp_comm_attach(ccqp_handle* h, const void* all_descs /* world * CCQP_COMM_DESC_BYTES */);
+ccqp_status ccqp_comm_prepare(ccqp_handle* h);
 ccqp_status ccqp_comm_detach(ccqp_handle* h);
 
 #ifdef __cplusplus
