@@ -8,7 +8,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libccqp_b200.so")
+# CCQP_B200_LIB: tuning hook, points at a variant build of the same library (tools/sweep_*.py)
+LIB_PATH = os.environ.get("CCQP_B200_LIB") or os.path.join(_HERE, "csrc", "libccqp_b200.so")
 
 MEM_HOST, MEM_DEVICE = 0, 1
 (IDENTITY, LOWER, UPPER, BOX, SPHERE, CONE_REF, SOC) = range(7)

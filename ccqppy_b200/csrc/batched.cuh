@@ -1,33 +1,65 @@
-// Batched mode: thousands of small independent box-constrained QPs (n <= 64), one CTA per problem
-// at a time, the whole solver loop of the reference inside one persistent kernel (no host round
-// trips).  Problem i is CCQPSolverX(tol,max_mv).solve(A[i], b[i], x0[i], BoxProjOp(n, lb[i], ub[i]))
+// Batched mode: thousands of small independent box-constrained QPs (n <= 64), one CTA (64 threads)
+// per problem at a time, the whole solver loop of the reference inside one persistent kernel (no
+// host round trips).  Problem i is CCQPSolverX(tol,max_mv).solve(A[i], b[i], x0[i], BoxProjOp(n, lb[i], ub[i]))
 // (solvers.py:94/220/393/583/719/878 with solution_spaces.py:280-366).
 //
 // Data path per problem (n = 64: 32 KB of A, 2 KB of vectors in, 512 B out):
-//   HBM --TMA row copies (cp.async.bulk, 64 x 512 B, one mbarrier)--> padded shared-memory tile
-//       --LDS.128--> registers: thread t keeps row t of A (64 doubles) for the whole solve.
-//   The tile is free as soon as the rows are in registers, so the NEXT problem's copy is issued
-//   immediately and lands while the current problem iterates (single buffer, full overlap).
-//   Each mat-vec is 64 FMAs per thread against x broadcast from shared memory (LDS.128, one
-//   wavefront per warp).  Dot products: warp shuffle tree, then the two warps exchange through
-//   shared memory.  Everything else (projection, axpy, step lengths, stopping tests) is per-thread
-//   register arithmetic.  Problems are handed out through an atomic counter (iteration counts
-//   differ per problem); results do not depend on the schedule.
+//   * A lives in REGISTERS for the whole solve.  Thread t = 4*rb + cb keeps the 4 x 16 sub-block
+//     A[4rb .. 4rb+3][16cb .. 16cb+15] (64 doubles), loaded straight from HBM/L2 with 16 256-bit
+//     read-only loads (each lane fetches one full 32-byte sector).  The problem AFTER the current one
+//     is pulled into L2 with one bulk-prefetch instruction (TMA engine, UBLKPF) while the current
+//     one iterates, so the register fill of the next problem is an L2 hit.
+//   * mat-vec: the input vector is published through a double-buffered 512-byte shared array (one
+//     barrier); a thread reads only its 16-entry slice (8 LDS.128), does 64 DFMAs (4 rows x 16
+//     columns, 8 independent chains) and the four lanes of a row block combine their 4 partial rows
+//     with a 2-stage exchange butterfly (3 SHFL.64 + 3 DADD) after which thread t holds y_t.
+//     Why not "thread t keeps row t" (the first version of this kernel): every thread then reads all
+//     64 entries of x per mat-vec, and a warp-wide LDS.128 occupies the shared-memory crossbar for
+//     4 cycles (512 bytes delivered) whether or not the lanes read the same address: 256 crossbar
+//     cycles per mat-vec per problem against 64 cycles of FP64 pipe.  ncu showed exactly that
+//     (shared-memory wavefronts 59 %, FP64 pipe 32 %; profiles/r01_ncu_full_first.csv).  The 4x16
+//     blocking cuts the crossbar work per mat-vec from 256 to ~80 cycles.
+//   * dot products: K <= 4 sums are reduced together with an exchange butterfly (6 SHFL.64 + 6 DADD
+//     for K = 3 instead of 15 + 15), then the two warps swap through shared memory (one barrier).
+//   * stopping tests compare the SQUARED residual with a host-computed threshold that is exactly
+//     equivalent to the reference's sqrt(.) < tol (sqrt is monotone), so no sqrt is on the
+//     per-iteration critical path; the reported residual is computed once at the end.
+//   * everything else (projection, axpy, step lengths) is per-thread register arithmetic, with the
+//     reference's rounding (compiled with -fmad=false; explicit fma() only in the sums).
+//   Problems are handed out through an atomic counter (iteration counts differ per problem);
+//   results do not depend on the schedule.
 //
 // Bounds: HBM bytes/problem = 8 n^2 + 32 n (+8 n for x0, + uniforms read by SPG);
 //         fp64 flops/problem = 2 n^2 * (mat-vecs executed).
 #pragma once
+#include <algorithm>
+#include <climits>
+#include <cstdlib>
+#include <cmath>
+#include <cstring>
 #include <functional>
 #include <string>
+#include <vector>
 
 #include "common.cuh"
 #include "../../include/ccqp_b200.h"
 
+#ifndef CCQP_BATCHED_ROWS
+#define CCQP_BATCHED_ROWS 8     // 8: 8x8 sub-blocks (3-stage exchange), 4: 4x16 sub-blocks (2-stage exchange)
+#endif
+
 namespace ccqp {
 
 constexpr int kBN = 64;                 // max unknowns per problem = threads per CTA
-constexpr int kBStride = kBN + 2;       // padded tile row (doubles): 528 B, conflict-free LDS.128
-constexpr int kBWindow = 64;
+constexpr int kBRows = CCQP_BATCHED_ROWS;    // sub-block of A held by one thread: kBRows x kBCols = 64 entries;
+constexpr int kBCols = kBN / kBRows;         // kBRows is also the number of lanes that share a row block
+constexpr int kBLog = (kBRows == 8) ? 3 : 2;
+constexpr int kBSlice = kBCols + 2;     // shared-memory pitch of one slice of the mat-vec input: consecutive slices
+                                        // start 16 bytes further into the 128-byte bank window, so the LDS.128 of
+                                        // a quarter-warp (kBRows distinct slices) is conflict-free
+constexpr int kBXs = kBRows * kBSlice;
+constexpr int kBWindow = 64;            // SPG window limit (generic path)
+constexpr int kBWinReg = 5;             // SPG window kept in registers when m == kBWinReg (the reference default)
 
 struct BatchedOut {
     double residual;
@@ -47,58 +79,148 @@ struct BatchedCtx {
     BatchedOut* out;        // [batch]
     unsigned* counter;      // work queue head
     int batch, n;
-    int tma_ok;             // rows can be moved with 16-byte bulk copies
+    int vec_ok;             // rows of A can be read with 256-bit loads (n % 4 == 0, 32-byte aligned base)
+    int pf_ok;              // whole problems can be bulk-prefetched into L2 (16-byte granularity)
     double tol, max_mv, step, tau, sig1, sig2;
+    double thr_lt;          // q <  thr_lt  <=>  sqrt(q) <  tol      (solvers.py:156 etc.)
+    double thr_le;          // q <= thr_le  <=>  sqrt(q) <= tol      (SPG, solvers.py:949)
+    int max_mv_i;           // mv >= max_mv_i  <=>  (double)mv >= max_mv
     int m;
 };
 
 struct BatchedSmem {
-    double tile[kBN * kBStride];
-    double xs[kBN];
+    double xs[2][kBXs];     // mat-vec input, double buffered; 16-entry slices padded by 16 bytes
     double red[2][2][4];    // [parity][warp][slot]
-    uint64_t mbar;
     int next;
 };
 
-// sum of up to 4 values over the 64 threads; result in every thread; ONE __syncthreads
-template <int K>
-__device__ __forceinline__ void cta64_sum(double (&a)[K], BatchedSmem& sm, int& parity) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int k = 0; k < K; ++k) a[k] = warp_sum(a[k]);
-    if (lane == 0) {
-#pragma unroll
-        for (int k = 0; k < K; ++k) sm.red[parity][warp][k] = a[k];
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < K; ++k) a[k] = sm.red[parity][0][k] + sm.red[parity][1][k];
-    parity ^= 1;
+// Shared-memory accesses of the solver loop go through 32-bit shared-space addresses computed once
+// per thread: with generic pointers the compiler re-derives the shared window base (S2UR
+// SR_CgaCtaId + ULEA, a scoreboard stall) in front of every access of the loop.
+struct BShared {
+    uint32_t xs_wr;     // where thread t publishes its entry (buffer 0)
+    uint32_t xs_rd;     // this thread's 16-entry slice (buffer 0)
+    uint32_t red;       // red[0][0][0]
+};
+constexpr uint32_t kBXsBytes = kBXs * 8;
+
+__device__ __forceinline__ void sts_f64(uint32_t addr, double v) {
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void lds_f64x2(uint32_t addr, double& x, double& y) {
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(x), "=d"(y) : "r"(addr) : "memory");
 }
 
-// y_t = sum_j a[j] * xs[j]   (xs complete in shared memory; 4 interleaved FMA chains)
-__device__ __forceinline__ double row_dot(const double (&a)[kBN], const double* xs) {
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-#pragma unroll
-    for (int j = 0; j < kBN; j += 4) {
-        const double2 u = *reinterpret_cast<const double2*>(xs + j);
-        const double2 v = *reinterpret_cast<const double2*>(xs + j + 2);
-        s0 = fma(a[j], u.x, s0);
-        s1 = fma(a[j + 1], u.y, s1);
-        s2 = fma(a[j + 2], v.x, s2);
-        s3 = fma(a[j + 3], v.y, s3);
+__device__ __forceinline__ double shfl_xor_f64(double v, int mask) { return __shfl_xor_sync(0xffffffffu, v, mask); }
+
+// Sum K (<= 4) values over the 64 threads; result in every thread; ONE __syncthreads.
+// Exchange butterfly: after the first stages each lane carries ONE of the K sums, so the tree
+// costs max(K,2)+3 shuffles and adds instead of 5K.  Fixed order => deterministic.
+template <int K>
+__device__ __forceinline__ void cta64_sum(double (&a)[K], const BShared& sh, int& parity) {
+    static_assert(K >= 1 && K <= 4, "K");
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double v;
+    int slot;            // which of the K sums this lane ends up carrying (lanes 0..3 are used)
+    if constexpr (K == 1) {
+        v = a[0] + shfl_xor_f64(a[0], 1);
+        v += shfl_xor_f64(v, 2);
+        slot = 0;
+    } else if constexpr (K == 2) {
+        const bool odd = lane & 1;
+        const double keep = odd ? a[1] : a[0], send = odd ? a[0] : a[1];
+        v = keep + shfl_xor_f64(send, 1);
+        v += shfl_xor_f64(v, 2);
+        slot = lane & 1;
+    } else {
+        const bool odd = lane & 1;
+        const double a3 = (K == 4) ? a[K - 1] : 0.0;
+        double k0 = odd ? a[2] : a[0], k1 = odd ? a3 : a[1];
+        const double s0 = odd ? a[0] : a[2], s1 = odd ? a[1] : a3;
+        k0 += shfl_xor_f64(s0, 1);
+        if (K == 4) k1 += shfl_xor_f64(s1, 1);
+        else { const double r = shfl_xor_f64(s1, 1); k1 = odd ? 0.0 : k1 + r; }   // slot 3 unused for K == 3
+        const bool up = lane & 2;
+        const double keep = up ? k1 : k0, send = up ? k0 : k1;
+        v = keep + shfl_xor_f64(send, 2);
+        slot = 2 * (lane & 1) + ((lane >> 1) & 1);
     }
-    return (s0 + s1) + (s2 + s3);
+    v += shfl_xor_f64(v, 4);
+    v += shfl_xor_f64(v, 8);
+    v += shfl_xor_f64(v, 16);
+    const uint32_t base = sh.red + (uint32_t)parity * 64u;      // red[parity]: 2 warps x 4 slots x 8 bytes
+    if (lane < 4 && slot < K) sts_f64(base + (uint32_t)(warp * 4 + slot) * 8u, v);
+    __syncthreads();
+    if constexpr (K == 1) {
+        a[0] = lds_f64(base) + lds_f64(base + 32);
+    } else {
+        double p0, p1, q0, q1;
+        lds_f64x2(base, p0, p1);
+        lds_f64x2(base + 32, q0, q1);
+        a[0] = p0 + q0; a[1] = p1 + q1;
+        if constexpr (K == 3) a[2] = lds_f64(base + 16) + lds_f64(base + 48);
+        if constexpr (K == 4) {
+            lds_f64x2(base + 16, p0, p1);
+            lds_f64x2(base + 48, q0, q1);
+            a[2] = p0 + q0; a[3] = p1 + q1;
+        }
+    }
+    parity ^= 1;
 }
 
 __device__ __forceinline__ double clampd(double t, double lo, double hi) { return t < lo ? lo : (t > hi ? hi : t); }
 
-// publish v as the mat-vec input and return (A v)_t
-__device__ __forceinline__ double matvec(const double (&a)[kBN], BatchedSmem& sm, double v) {
-    __syncthreads();            // previous readers of xs are done
-    sm.xs[threadIdx.x] = v;
+// Publish v (entry t of the mat-vec input) and return (A v)_t.
+// Thread t = kBRows*rb + cb holds the kBRows x kBCols sub-block (row block rb, column block cb).
+// Register row i holds row kBRows*rb + (i ^ cb) of A (the fill permutes the rows), so that in the
+// exchange butterfly below the partial sums a lane keeps and the ones it sends sit in FIXED
+// registers: no per-lane selects.  Stage "xor h" (h = kBRows/2, ..., 1): a lane keeps the rows whose
+// bit h agrees with its own cb and receives the partner's partial sums of exactly those rows; after
+// the last stage lane cb holds row 0 ^ cb = cb complete, i.e. thread t holds y_t.
+// `act` is false for the padding threads t >= n: they publish an exact zero whatever v is, so a
+// non-finite step length cannot leak NaNs into the active rows through the zero columns of A.
+__device__ __forceinline__ double matvec(const double (&a)[kBRows][kBCols], const BShared& sh, int& xpar, bool act,
+                                         double v) {
+    const uint32_t boff = (uint32_t)xpar * kBXsBytes;
+    sts_f64(sh.xs_wr + boff, act ? v : 0.0);
     __syncthreads();
-    return row_dot(a, sm.xs);
+    const uint32_t xp = sh.xs_rd + boff;
+    xpar ^= 1;
+    double x[kBCols];
+#pragma unroll
+    for (int j = 0; j < kBCols; j += 2) lds_f64x2(xp + j * 8, x[j], x[j + 1]);
+    double s[kBRows];
+    if constexpr (kBRows == 8) {      // 8 rows: one chain per row
+#pragma unroll
+        for (int r = 0; r < kBRows; ++r) s[r] = a[r][0] * x[0];
+#pragma unroll
+        for (int j = 1; j < kBCols; ++j)
+#pragma unroll
+            for (int r = 0; r < kBRows; ++r) s[r] = fma(a[r][j], x[j], s[r]);
+    } else {                          // 4 rows: two chains per row
+        double acc[kBRows][2];
+#pragma unroll
+        for (int r = 0; r < kBRows; ++r) { acc[r][0] = a[r][0] * x[0]; acc[r][1] = a[r][1] * x[1]; }
+#pragma unroll
+        for (int j = 2; j < kBCols; j += 2)
+#pragma unroll
+            for (int r = 0; r < kBRows; ++r) {
+                acc[r][0] = fma(a[r][j], x[j], acc[r][0]);
+                acc[r][1] = fma(a[r][j + 1], x[j + 1], acc[r][1]);
+            }
+#pragma unroll
+        for (int r = 0; r < kBRows; ++r) s[r] = acc[r][0] + acc[r][1];
+    }
+#pragma unroll
+    for (int h = kBRows / 2; h >= 1; h >>= 1)
+#pragma unroll
+        for (int i = 0; i < h; ++i) s[i] += shfl_xor_f64(s[i + h], h);
+    return s[0];
 }
 
 struct BState {                 // per-thread view of one problem (thread t <-> unknown t)
@@ -107,41 +229,82 @@ struct BState {                 // per-thread view of one problem (thread t <-> 
     bool act;                   // t < n
 };
 
-template <int SOLVER>
-__device__ __forceinline__ void solve_one(const BatchedCtx& c, const double (&a)[kBN], BatchedSmem& sm, const BState& s,
-                                          const double* uni, double& xsol, BatchedOut& o) {
-    int par = 0;
+// SPG's deque(maxlen=m) (solvers.py:931).  Only max() over the contents is ever taken (:953), so the
+// order of the entries is irrelevant: for the reference default m = 5 the window is a 5-register
+// shift register padded with -inf (max ignores the padding; 4 moves + 4 compares per iteration);
+// any other m uses a ring buffer in local memory.
+template <bool REG>
+struct SpgWindow {
+    double w[REG ? kBWinReg : kBWindow];
+    int count, head;
+    __device__ __forceinline__ void init(double f) {
+        if constexpr (REG) {
+#pragma unroll
+            for (int j = 0; j < kBWinReg - 1; ++j) w[j] = -INFINITY;
+            w[kBWinReg - 1] = f;
+        } else { w[0] = f; count = 1; head = 0; }
+    }
+    __device__ __forceinline__ double max() const {
+        if constexpr (REG) {
+            double fmax = w[0];
+#pragma unroll
+            for (int j = 1; j < kBWinReg; ++j) fmax = fmax > w[j] ? fmax : w[j];
+            return fmax;
+        } else {
+            double fmax = w[0];
+            for (int j = 1; j < count; ++j) fmax = fmax > w[j] ? fmax : w[j];
+            return fmax;
+        }
+    }
+    __device__ __forceinline__ void push(double f, int m) {
+        if constexpr (REG) {
+#pragma unroll
+            for (int j = 0; j < kBWinReg - 1; ++j) w[j] = w[j + 1];
+            w[kBWinReg - 1] = f;
+        } else {
+            if (count < m) { w[count] = f; count++; }
+            else { w[head] = f; head = (head + 1 == m) ? 0 : head + 1; }
+        }
+    }
+};
+
+template <int SOLVER, bool WREG>
+__device__ __forceinline__ void solve_one(const BatchedCtx& c, const double (&a)[kBRows][kBCols], const BShared& sm,
+                                          const BState& s, const double* uni, int& par, int& xpar, double& xsol,
+                                          BatchedOut& o) {
     int mv = 0, gemv = 0, iters = 0, draws = 0, status = 0;
     double res = NAN;
-    const double tol = c.tol, maxmv = c.max_mv;
+    const int maxmv = c.max_mv_i;
     auto resid2 = [&](double x, double g) { const double d = s.cs * (x - clampd(x - kGd * g, s.lo, s.hi)); return d * d; };
 
     if constexpr (SOLVER == CCQP_SOLVER_PGD || SOLVER == CCQP_SOLVER_BBPGD || SOLVER == CCQP_SOLVER_BBPGDF) {
         // solvers.py:114-170, 606-669, 741-819
         double x = s.x0, xm = s.x0, g, gm, xmin = s.x0, gmin = s.x0, resmin = INFINITY;
-        gm = matvec(a, sm, xm) + s.b; gemv++; mv = 1;
+        gm = matvec(a, sm, xpar, s.act, xm) + s.b; gemv++; mv = 1;
         double r1[1] = {resid2(xm, gm)};
         cta64_sum<1>(r1, sm, par);
-        res = sqrt(r1[0]);
-        if (res >= tol) {
+        double res2 = r1[0];
+        if (!(res2 < c.thr_lt)) {
             double step = c.step;
             if (SOLVER != CCQP_SOLVER_PGD) {
-                const double ag = matvec(a, sm, gm); gemv++;          // not counted (:635)
+                const double ag = matvec(a, sm, xpar, s.act, gm); gemv++;          // not counted (:635)
                 double q[2] = {gm * gm, gm * ag};
                 cta64_sum<2>(q, sm, par);
                 step = q[0] / q[1];
             }
             for (;;) {
                 x = clampd(xm - step * gm, s.lo, s.hi);
-                g = matvec(a, sm, x) + s.b; gemv++; mv++;
-                if ((double)mv >= maxmv) break;
+                g = matvec(a, sm, xpar, s.act, x) + s.b; gemv++; mv++;
+                if (mv >= maxmv) break;
                 const double sx = x - xm, sy = g - gm;
                 double q[3] = {resid2(x, g), sx * sx, sx * sy};
-                cta64_sum<3>(q, sm, par);
-                res = sqrt(q[0]);
+                if (SOLVER == CCQP_SOLVER_PGD) { double q1[1] = {q[0]}; cta64_sum<1>(q1, sm, par); q[0] = q1[0]; }
+                else cta64_sum<3>(q, sm, par);
+                res2 = q[0];
                 iters++;
-                if (res < tol) break;
+                if (res2 < c.thr_lt) break;
                 if (SOLVER == CCQP_SOLVER_BBPGDF) {                   // :793-800
+                    res = sqrt(res2);
                     if (res < resmin) { resmin = res; xmin = x; gmin = g; }
                     if (step < 10 * kEps) {
                         x = clampd(xmin - kGd * gmin, s.lo, s.hi);
@@ -155,32 +318,31 @@ __device__ __forceinline__ void solve_one(const BatchedCtx& c, const double (&a)
                 xm = x; gm = g;
             }
         }
+        res = sqrt(res2);
         xsol = x;
     } else if constexpr (SOLVER == CCQP_SOLVER_SPG) {
         // solvers.py:906-975
         double x = s.x0;
-        double g = matvec(a, sm, x) + s.b; gemv++;
-        const double ag = matvec(a, sm, g); gemv++;
+        double g = matvec(a, sm, xpar, s.act, x) + s.b; gemv++;
+        const double ag = matvec(a, sm, xpar, s.act, g); gemv++;
         double q0[3] = {g * x, g * g, g * ag};
         cta64_sum<3>(q0, sm, par);
         double f = q0[0];
         double alpha = q0[1] / q0[2];
         mv = 2;
-        double window[kBWindow];
-        int wcount = 1, whead = 0;
-        window[0] = f;
+        SpgWindow<WREG> win;
+        win.init(f);
         double dd_rep = NAN;
         for (;;) {
             const double d = clampd(x - alpha * g, s.lo, s.hi) - x;
-            const double ad = matvec(a, sm, d); gemv++; mv++;
-            if ((double)mv >= maxmv) break;
+            const double ad = matvec(a, sm, xpar, s.act, d); gemv++; mv++;
+            if (mv >= maxmv) break;
             double q[3] = {d * d, d * ad, d * g};
             cta64_sum<3>(q, sm, par);
             const double dd = q[0], dAd = q[1], dg = q[2];
             dd_rep = dd;
-            if (sqrt(dd) <= tol) break;
-            double fmax = window[0];
-            for (int j = 1; j < wcount; ++j) fmax = fmax > window[j] ? fmax : window[j];
+            if (dd <= c.thr_le) break;                                // sqrt(dd) <= tol (:949)
+            const double fmax = win.max();
             const double xi = (fmax - f) / dAd;
             const double beta = -dg / dAd;
             const double bhat = c.tau * beta + sqrt((c.tau * c.tau) * (beta * beta) + 2 * xi);
@@ -192,8 +354,7 @@ __device__ __forceinline__ void solve_one(const BatchedCtx& c, const double (&a)
             x += bk * d;
             g += bk * ad;
             f += bk * bk * dg + 0.5 * (bk * bk) * dAd;                // :963 as written
-            if (wcount < c.m) window[wcount++] = f;
-            else { window[whead] = f; whead = (whead + 1) % c.m; }
+            win.push(f, c.m);
             alpha = dd / dAd;
             iters++;
         }
@@ -204,40 +365,32 @@ __device__ __forceinline__ void solve_one(const BatchedCtx& c, const double (&a)
         constexpr bool AR = SOLVER == CCQP_SOLVER_APGD_AR;
         double x = s.x0, y = s.x0, xp = s.x0, xhat = 1.0, axp = 0.0;
         const double d0 = s.act ? (s.x0 - 1.0) : 0.0;
-        const double ad0 = matvec(a, sm, d0); gemv++; mv = 1;
+        const double ad0 = matvec(a, sm, xpar, s.act, d0); gemv++; mv = 1;
         double q0[2] = {ad0 * ad0, d0 * d0};
         cta64_sum<2>(q0, sm, par);
         double L = sqrt(q0[0]) / sqrt(q0[1]);
-        double t = 1.0 / L, theta = 1.0, resmin = INFINITY;
+        double t = 1.0 / L, theta = 1.0, resmin = INFINITY, res2 = NAN;
         for (;;) {
-            const double ay = matvec(a, sm, y); gemv++; mv++;
-            if ((double)mv >= maxmv) break;
+            const double ay = matvec(a, sm, xpar, s.act, y); gemv++; mv++;
+            if (mv >= maxmv) break;
             const double g = ay + s.b;
             xp = clampd(y - t * g, s.lo, s.hi);
-            double r12[2] = {y * ay, y * s.b};
             bool have12 = false;
             double rt1 = 0.0, rt2 = 0.0;
             for (;;) {
-                axp = matvec(a, sm, xp); gemv++; mv++;
-                const bool lim = (double)mv >= maxmv;
+                axp = matvec(a, sm, xpar, s.act, xp); gemv++; mv++;
+                const bool lim = mv >= maxmv;
                 const double df = xp - y;
-                if (!have12) {       // fold the two outer sums into the first inner reduction
-                    double q[6] = {xp * axp, xp * s.b, g * df, df * df, r12[0], r12[1]};
-                    // 6 slots: two rounds of <=4
-                    double qa[4] = {q[0], q[1], q[2], q[3]};
-                    double qb[2] = {q[4], q[5]};
-                    cta64_sum<4>(qa, sm, par);
+                double qa[4] = {xp * axp, xp * s.b, g * df, df * df};
+                cta64_sum<4>(qa, sm, par);
+                if (!have12) {       // the two outer sums (:285-286) ride along with the first inner reduction
+                    double qb[2] = {y * ay, y * s.b};
                     cta64_sum<2>(qb, sm, par);
                     rt1 = qb[0] * 0.5; rt2 = qb[1];
                     have12 = true;
-                    if (lim) break;
-                    if ((qa[0] * 0.5 + qa[1]) <= (rt1 + rt2 + qa[2] + 0.5 * L * qa[3])) break;
-                } else {
-                    double qa[4] = {xp * axp, xp * s.b, g * df, df * df};
-                    cta64_sum<4>(qa, sm, par);
-                    if (lim) break;
-                    if ((qa[0] * 0.5 + qa[1]) <= (rt1 + rt2 + qa[2] + 0.5 * L * qa[3])) break;
                 }
+                if (lim) break;      // leaves the inner loop only (:292-293)
+                if ((qa[0] * 0.5 + qa[1]) <= (rt1 + rt2 + qa[2] + 0.5 * L * qa[3])) break;
                 L *= 2;
                 t = 1.0 / L;
                 xp = clampd(y - t * g, s.lo, s.hi);
@@ -246,11 +399,12 @@ __device__ __forceinline__ void solve_one(const BatchedCtx& c, const double (&a)
             const double beta = theta * (1 - theta) / (theta * theta + theta_n);
             double yn = (1 + beta) * xp - beta * x;
             double q[2] = {resid2(xp, axp + s.b), AR ? g * (xp - x) : 0.0};
-            cta64_sum<2>(q, sm, par);
-            res = sqrt(q[0]);
+            if (AR) cta64_sum<2>(q, sm, par);
+            else { double q1[1] = {q[0]}; cta64_sum<1>(q1, sm, par); q[0] = q1[0]; }
+            res2 = q[0];
             iters++;
-            if (AR && res < resmin) { resmin = res; xhat = xp; }
-            if (res < tol) break;
+            if (AR) { res = sqrt(res2); if (res < resmin) { resmin = res; xhat = xp; } }
+            if (res2 < c.thr_lt) break;
             if (AR && q[1] > 0) { yn = xp; theta_n = 1; }
             L *= 0.9;
             t = 1.0 / L;
@@ -258,52 +412,67 @@ __device__ __forceinline__ void solve_one(const BatchedCtx& c, const double (&a)
             { const double tmp = x; x = xp; xp = tmp; }   // buffer swap (:332-334)
             theta = theta_n;
         }
+        res = sqrt(res2);
         xsol = AR ? xhat : xp;
     }
     o.residual = res;
     o.mv = mv; o.gemv = gemv; o.iters = iters; o.draws = draws;
-    o.converged = ((double)mv < maxmv) ? 1 : 0;
+    o.converged = (mv < maxmv) ? 1 : 0;
     o.status = status;
 }
 
-template <int SOLVER>
-__global__ void __launch_bounds__(kBN, 4) batched_kernel(const BatchedCtx c) {
-    __shared__ __align__(128) BatchedSmem sm;
-    const int t = threadIdx.x, n = c.n;
-    unsigned phase = 0;
-    if (t == 0) { mbar_init(&sm.mbar, 1); mbar_fence_init(); }
-    __syncthreads();
+#ifndef CCQP_BATCHED_CTAS
+#define CCQP_BATCHED_CTAS 6     // resident CTAs per SM the register budget is cut for (6 -> 168 registers)
+#endif
+constexpr int batched_min_ctas(int solver) {
+    return (solver == CCQP_SOLVER_PGD || solver == CCQP_SOLVER_BBPGD || solver == CCQP_SOLVER_SPG) ? CCQP_BATCHED_CTAS : 5;
+}
 
-    auto issue_load = [&](int prob) {   // rows of A[prob] -> padded tile
-        if (c.tma_ok) {
-            if (t == 0) mbar_expect_tx(&sm.mbar, (uint32_t)(n * n * 8));
-            if (t < n) bulk_g2s(sm.tile + t * kBStride, c.A + ((size_t)prob * n + t) * n, (uint32_t)(n * 8), &sm.mbar);
-        }
+template <int SOLVER, bool WREG>
+__global__ void __launch_bounds__(kBN, batched_min_ctas(SOLVER)) batched_kernel(const BatchedCtx c) {
+    __shared__ __align__(16) BatchedSmem sm;
+    const int t = threadIdx.x, n = c.n;
+    const int cb = t & (kBRows - 1), row0 = kBRows * (t >> kBLog), col0 = kBCols * cb;
+    int par = 0, xpar = 0;
+    BShared sh;
+    sh.xs_wr = smem_u32(&sm.xs[0][t + 2 * (t / kBCols)]);
+    sh.xs_rd = smem_u32(&sm.xs[0][kBSlice * cb]);
+    sh.red = smem_u32(&sm.red[0][0][0]);
+    const size_t prob_elems = (size_t)n * n;
+
+    auto prefetch_l2 = [&](int prob) {      // the whole next problem, one instruction (TMA engine)
+        if (c.pf_ok && t == 0)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(c.A + (size_t)prob * prob_elems),
+                         "r"((unsigned)(prob_elems * 8)) : "memory");
     };
-    int cur;
     if (t == 0) sm.next = (int)atomicAdd(c.counter, 1u);
     __syncthreads();
-    cur = sm.next;
-    if (cur < c.batch) { fence_proxy_async(); issue_load(cur); }
+    int cur = sm.next;
     while (cur < c.batch) {
-        double a[kBN];
-        if (c.tma_ok) {
-            mbar_wait(&sm.mbar, phase);
-            phase ^= 1u;
-        } else {
-            __syncthreads();
-            const double* Ap = c.A + (size_t)cur * n * n;
-            for (int idx = t; idx < n * n; idx += kBN) sm.tile[(idx / n) * kBStride + (idx % n)] = Ap[idx];
-            __syncthreads();
-        }
+        __syncthreads();                       // everyone has read sm.next
+        if (t == 0) sm.next = (int)atomicAdd(c.counter, 1u);
+        // ---- register fill: this thread's sub-block; register row r <- row row0 + (r ^ cb) (see matvec)
+        double a[kBRows][kBCols];
+        const double* Ap = c.A + (size_t)cur * prob_elems;
+        if (c.vec_ok) {
 #pragma unroll
-        for (int j = 0; j < kBN; j += 2) {
-            if (t < n && j + 1 < n) {
-                const double2 v = *reinterpret_cast<const double2*>(sm.tile + t * kBStride + j);
-                a[j] = v.x; a[j + 1] = v.y;
-            } else if (t < n && j < n) {
-                a[j] = sm.tile[t * kBStride + j]; a[j + 1] = 0.0;
-            } else { a[j] = 0.0; a[j + 1] = 0.0; }
+            for (int r = 0; r < kBRows; ++r) {
+#pragma unroll
+                for (int j = 0; j < kBCols; j += 4) {
+                    const int row = row0 + (r ^ cb);
+                    if (row < n && col0 + j < n) {
+                        double v[4];
+                        ldg256_stream<false>(Ap + (size_t)row * n + col0 + j, v);
+                        a[r][j] = v[0]; a[r][j + 1] = v[1]; a[r][j + 2] = v[2]; a[r][j + 3] = v[3];
+                    } else { a[r][j] = 0.0; a[r][j + 1] = 0.0; a[r][j + 2] = 0.0; a[r][j + 3] = 0.0; }
+                }
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < kBRows; ++r)
+#pragma unroll
+                for (int j = 0; j < kBCols; ++j)
+                    a[r][j] = (row0 + (r ^ cb) < n && col0 + j < n) ? ldg_stream(Ap + (size_t)(row0 + (r ^ cb)) * n + col0 + j) : 0.0;
         }
         BState s;
         s.act = t < n;
@@ -313,15 +482,14 @@ __global__ void __launch_bounds__(kBN, 4) batched_kernel(const BatchedCtx c) {
         s.hi = s.act ? c.ub[vo] : 0.0;
         s.x0 = (s.act && c.x0) ? c.x0[vo] : 0.0;
         s.cs = 1.0 / (3 * (double)n * kGd);
-        __syncthreads();                       // every thread has its row: the tile is free
-        if (t == 0) sm.next = (int)atomicAdd(c.counter, 1u);
         __syncthreads();
         const int nxt = sm.next;
-        if (nxt < c.batch) { fence_proxy_async(); issue_load(nxt); }   // lands while we iterate
+        if (nxt < c.batch) prefetch_l2(nxt);   // lands in L2 while we iterate
 
         double xsol = 0.0;
         BatchedOut o;
-        solve_one<SOLVER>(c, a, sm, s, c.uniforms ? c.uniforms + (size_t)cur * c.n_uniforms : nullptr, xsol, o);
+        solve_one<SOLVER, WREG>(c, a, sh, s, c.uniforms ? c.uniforms + (size_t)cur * c.n_uniforms : nullptr, par, xpar,
+                                xsol, o);
         if (s.act) c.x_out[vo] = xsol;
         if (t == 0) c.out[cur] = o;
         cur = nxt;
@@ -331,15 +499,43 @@ __global__ void __launch_bounds__(kBN, 4) batched_kernel(const BatchedCtx c) {
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-template <int SOLVER>
+// Smallest double q >= 0 with pred(sqrt(q)) false ... expressed through the bit pattern: for
+// non-negative doubles the IEEE ordering equals the ordering of the bit patterns, and sqrt is
+// monotone and correctly rounded on both host and device, so the reference's test on sqrt(q)
+// is equivalent to a comparison of q with a threshold found by bisection.
+inline double sqrt_threshold(double tol, bool strict) {
+    // strict:  returns thr with  (q <  thr) <=> (sqrt(q) <  tol)
+    // !strict: returns thr with  (q <= thr) <=> (sqrt(q) <= tol)
+    if (tol != tol) return NAN;                                   // every comparison is false
+    auto holds = [&](unsigned long long bits) {
+        double q; std::memcpy(&q, &bits, 8);
+        const double r = std::sqrt(q);
+        return strict ? (r < tol) : (r <= tol);
+    };
+    const unsigned long long inf_bits = 0x7ff0000000000000ULL;
+    if (!holds(0)) return strict ? 0.0 : -1.0;                    // never true for q >= 0
+    if (holds(inf_bits)) return strict ? NAN : INFINITY;          // tol = +inf (strict: inf < inf is false, handled below)
+    unsigned long long lo = 0, hi = inf_bits;                     // holds(lo), !holds(hi)
+    while (hi - lo > 1) {
+        const unsigned long long mid = lo + (hi - lo) / 2;
+        if (holds(mid)) lo = mid; else hi = mid;
+    }
+    double out;
+    const unsigned long long pick = strict ? hi : lo;
+    std::memcpy(&out, &pick, 8);
+    return out;
+}
+
+template <int SOLVER, bool WREG>
 inline cudaError_t launch_batched(const BatchedCtx& c, int sm_count, cudaStream_t stream) {
     int per_sm = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, batched_kernel<SOLVER>, kBN, 0);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, batched_kernel<SOLVER, WREG>, kBN, 0);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
+    if (const char* e = getenv("CCQP_BATCHED_CTAS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(e)));   // tuning hook
     long long grid = (long long)sm_count * per_sm;
     if (grid > c.batch) grid = c.batch;
-    batched_kernel<SOLVER><<<(unsigned)grid, kBN, 0, stream>>>(c);
+    batched_kernel<SOLVER, WREG><<<(unsigned)grid, kBN, 0, stream>>>(c);
     return cudaGetLastError();
 }
 
@@ -392,19 +588,28 @@ inline int batched_solve(cudaStream_t stream, int sm_count, void*, size_t, int s
     c.n_uniforms = (solver == CCQP_SOLVER_SPG) ? n_uniforms : 0;
     c.out = dout; c.counter = counter;
     c.batch = (int)batch; c.n = (int)n;
-    c.tma_ok = ((n * 8) % 16 == 0 && (reinterpret_cast<uintptr_t>(c.A) & 15) == 0) ? 1 : 0;
+    c.vec_ok = (n % 4 == 0 && (reinterpret_cast<uintptr_t>(c.A) & 31) == 0) ? 1 : 0;
+    c.pf_ok = ((n * n * 8) % 16 == 0 && (reinterpret_cast<uintptr_t>(c.A) & 15) == 0) ? 1 : 0;
     c.tol = prm.tol; c.max_mv = prm.max_mv; c.step = prm.step_size;
     c.tau = prm.tau; c.sig1 = prm.sigma1; c.sig2 = prm.sigma2; c.m = prm.m;
+    c.thr_lt = sqrt_threshold(prm.tol, true);
+    c.thr_le = sqrt_threshold(prm.tol, false);
+    c.max_mv_i = (prm.max_mv != prm.max_mv || prm.max_mv >= 2147483000.0) ? INT_MAX
+                 : (prm.max_mv <= -2147483000.0 ? INT_MIN : (int)std::ceil(prm.max_mv));
     BCU(cudaMemsetAsync(counter, 0, 256, stream));
     BCU(cudaEventRecord(ev0, stream));
     cudaError_t le;
+    const bool wreg = prm.m == kBWinReg;
     switch (solver) {
-        case CCQP_SOLVER_PGD: le = launch_batched<CCQP_SOLVER_PGD>(c, sm_count, stream); break;
-        case CCQP_SOLVER_APGD: le = launch_batched<CCQP_SOLVER_APGD>(c, sm_count, stream); break;
-        case CCQP_SOLVER_APGD_AR: le = launch_batched<CCQP_SOLVER_APGD_AR>(c, sm_count, stream); break;
-        case CCQP_SOLVER_BBPGD: le = launch_batched<CCQP_SOLVER_BBPGD>(c, sm_count, stream); break;
-        case CCQP_SOLVER_BBPGDF: le = launch_batched<CCQP_SOLVER_BBPGDF>(c, sm_count, stream); break;
-        case CCQP_SOLVER_SPG: le = launch_batched<CCQP_SOLVER_SPG>(c, sm_count, stream); break;
+        case CCQP_SOLVER_PGD: le = launch_batched<CCQP_SOLVER_PGD, true>(c, sm_count, stream); break;
+        case CCQP_SOLVER_APGD: le = launch_batched<CCQP_SOLVER_APGD, true>(c, sm_count, stream); break;
+        case CCQP_SOLVER_APGD_AR: le = launch_batched<CCQP_SOLVER_APGD_AR, true>(c, sm_count, stream); break;
+        case CCQP_SOLVER_BBPGD: le = launch_batched<CCQP_SOLVER_BBPGD, true>(c, sm_count, stream); break;
+        case CCQP_SOLVER_BBPGDF: le = launch_batched<CCQP_SOLVER_BBPGDF, true>(c, sm_count, stream); break;
+        case CCQP_SOLVER_SPG:
+            le = wreg ? launch_batched<CCQP_SOLVER_SPG, true>(c, sm_count, stream)
+                      : launch_batched<CCQP_SOLVER_SPG, false>(c, sm_count, stream);
+            break;
         default: return CCQP_ERR_INVALID_ARG;
     }
     BCU(le);

@@ -101,3 +101,27 @@ def test_batched_large_properties():
     s1 = make_solver(pr.BBPGD, tol, 5000).solve_batched(A, b, lb, ub)
     s2 = make_solver(pr.BBPGD, tol, 5000).solve_batched(A[perm].contiguous(), b[perm].contiguous(), lb, ub)
     assert torch.equal(s1.solution[perm], s2.solution)
+
+
+@pytest.mark.parametrize("m,tau,sig1,sig2", [(1, 0.5, 0.01, 0.5), (3, 0.4, 0.02, 0.6), (5, 0.5, 0.01, 0.5), (8, 0.7, 0.05, 0.9)])
+def test_batched_spg_hyperparameters(m, tau, sig1, sig2):
+    """SPG's window length and step bounds (solvers.py:856): m = 5 runs the register-window kernel,
+    every other m the generic one; both must reproduce the oracle problem by problem."""
+    from ccqppy_b200 import solvers
+    batch, n, K = 24, 64, 600
+    A, b, lb, ub = make_batch(batch, n, seed0=40)
+    s = solvers.CCQPSolverSPG(1e-8, 5000, m=m, tau=tau, sigma1=sig1, sigma2=sig2)
+    s.quiet = True
+    s.solve_batched(A, b, lb, ub, seeds=np.arange(batch), n_uniforms=K)
+    same = 0
+    for i in range(batch):
+        tab = pr.Table().add(pr.BOX, n, lb[i], ub[i])
+        o = orc.solve(pr.SPG, A[i], b[i], blocks=tab.blocks, params=tab.params, tol=1e-8, max_mv=5000, m=m, tau=tau,
+                      sigma1=sig1, sigma2=sig2, uniforms=pr.spg_uniforms(i, K))
+        assert bool(s.solution_converged[i]) == o["converged"]
+        mv = int(s.solution_num_matrix_vector_multiplications[i])
+        assert abs(mv - o["mv"]) <= max(2, round(0.1 * o["mv"]))
+        if mv == o["mv"]:
+            same += 1
+            assert np.linalg.norm(s.solution[i] - o["solution"]) <= 1e-9 * np.linalg.norm(o["solution"])
+    assert same >= 0.9 * batch
