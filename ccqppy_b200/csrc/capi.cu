@@ -49,7 +49,7 @@ struct ccqp_handle {
     DevBuf lo, hi, ekind, bkind, boff, bdim, bpar, small_ids, big_ids;
     int nblk = 0, nsmall = 0, nbig = 0, has_cone_ref = 0;
     // workspaces
-    DevBuf work, partials, andparts, flags, out_dev, uniforms, batched_ws;
+    DevBuf work, partials, flags, out_dev, uniforms, batched_ws, dbg;
     void* out_host = nullptr;   // pinned
     long long npad = 0;
     long long launches = 0;
@@ -105,8 +105,7 @@ ccqp_status ensure_work(ccqp_handle* h) {
         h->npad = npad;
     }
     CU(h, h->partials.ensure((size_t)2 * h->sm_count * kMaxRed * 8));
-    CU(h, h->andparts.ensure((size_t)2 * h->sm_count * 8));
-    CU(h, h->flags.ensure(256));
+    CU(h, h->flags.ensure(kSyncBytes));
     CU(h, h->out_dev.ensure(sizeof(DenseOut)));
     if (!h->out_host) CU(h, cudaMallocHost(&h->out_host, 4096));
     return CCQP_OK;
@@ -152,16 +151,15 @@ void fill_ctx(ccqp_handle* h, DenseCtx& c, const Tiling& t) {
     c.T.nbig = h->nbig; c.T.big_ids = h->big_ids.as<int>();
     c.T.has_cone_ref = h->has_cone_ref;
     c.T.all_elementwise = (h->nsmall + h->nbig) == 0;
-    c.T.e0 = (int)h->row0; c.T.e1 = (int)(h->row0 + h->nrows);
-    c.partials = h->partials.as<double>();
-    c.andparts = h->andparts.as<unsigned long long>();
-    c.bar_counter = h->flags.as<unsigned>();
-    c.abort_flag = h->flags.as<unsigned>() + 8;
+    c.T.e0 = 0; c.T.e1 = (int)h->n;   // every rank repeats the elementwise work on the full vectors
+    c.gs.partials = h->partials.as<unsigned long long>();
+    c.gs.arrive = reinterpret_cast<unsigned*>(h->flags.as<char>() + kSyncArriveOff);
+    c.gs.abort = reinterpret_cast<unsigned*>(h->flags.as<char>() + kSyncAbortOff);
+    c.gs.go = reinterpret_cast<unsigned*>(h->flags.as<char>() + kSyncGoOff);
+    c.gs.result = reinterpret_cast<unsigned long long*>(h->flags.as<char>() + kSyncResultOff);
     c.x.world = h->world; c.x.rank = h->rank;
     for (int s = 0; s < kMaxWorld; ++s) c.x.base[s] = (s < h->world) ? h->peer_base[s] : nullptr;
     if (h->world == 1) c.x.base[0] = h->work.as<char>();
-    c.x.local_arrive = h->flags.as<unsigned>() + 16;
-    c.x.local_go = h->flags.as<unsigned>() + 24;
     c.out = h->out_dev.as<DenseOut>();
     c.CW = t.CW; c.SW = t.SW; c.np = t.np; c.nseg = t.nseg; c.rows_max = t.rows_max;
     c.evict_first = ((double)h->nrows * (double)h->n * 8.0 > 96.0 * 1024 * 1024) ? 1 : 0;
@@ -175,7 +173,7 @@ ccqp_status launch_dense(ccqp_handle* h, DenseCtx& c, const Tiling& t, bool coop
         CU(h, cudaFuncSetAttribute(dense_kernel<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
         configured = 220 * 1024;
     }
-    if (cooperative) CU(h, cudaMemsetAsync(h->flags.p, 0, 256, h->stream));   // barrier counters
+    if (cooperative) CU(h, cudaMemsetAsync(h->flags.p, 0, kSyncBytes, h->stream));   // barrier counters
     void* args[] = {&c};
     if (cooperative)
         CU(h, cudaLaunchCooperativeKernel((const void*)dense_kernel<OP>, dim3(t.grid), dim3(kDenseThreads), args, t.smem, h->stream));
@@ -250,8 +248,8 @@ ccqp_status ccqp_destroy(ccqp_handle* h) {
     cudaStreamSynchronize(h->stream);
     if (h->world > 1) ccqp_comm_detach(h);
     DevBuf* bufs[] = {&h->a_own, &h->lo, &h->hi, &h->ekind, &h->bkind, &h->boff, &h->bdim, &h->bpar, &h->small_ids,
-                      &h->big_ids, &h->work, &h->partials, &h->andparts, &h->flags, &h->out_dev, &h->uniforms,
-                      &h->batched_ws};
+                      &h->big_ids, &h->work, &h->partials, &h->flags, &h->out_dev, &h->uniforms,
+                      &h->batched_ws, &h->dbg};
     for (DevBuf* b : bufs) b->release();
     if (h->out_host) cudaFreeHost(h->out_host);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -400,6 +398,12 @@ ccqp_status ccqp_solve(ccqp_handle* h, int solver, const ccqp_params* params, co
         }
         c.n_uniforms = n_uniforms;
     }
+    const bool dbg_timing = getenv("CCQP_DEBUG_TIMING") != nullptr;
+    if (dbg_timing) {
+        CU(h, h->dbg.ensure(kDbgSlots * kDbgIters * 8));
+        CU(h, cudaMemsetAsync(h->dbg.p, 0, kDbgSlots * kDbgIters * 8, h->stream));
+        c.dbg = h->dbg.as<long long>();
+    }
     const long long launches0 = h->launches;
     CU(h, cudaEventRecord(h->ev0, h->stream));
     if ((st = launch_by_solver(h, solver, c, t)) != CCQP_OK) return st;
@@ -413,6 +417,22 @@ ccqp_status ccqp_solve(ccqp_handle* h, int solver, const ccqp_params* params, co
     }
     float ms = 0.f;
     CU(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    if (dbg_timing && h->rank == 0) {      // mean phase durations of CTA 0 over iterations 8..39, microseconds
+        std::vector<long long> t(kDbgSlots * kDbgIters);
+        CU(h, cudaMemcpy(t.data(), h->dbg.p, t.size() * 8, cudaMemcpyDeviceToHost));
+        double acc[5] = {0, 0, 0, 0, 0};
+        int cnt = 0;
+        for (int it = 8; it < 40; ++it) {
+            const long long* r = &t[it * kDbgSlots];
+            const long long* nx = &t[(it + 1) * kDbgSlots];
+            if (!r[0] || !r[4] || !nx[0]) continue;
+            for (int s = 0; s < 4; ++s) acc[s] += (r[s + 1] - r[s]) * 1e-3;
+            acc[4] += (nx[0] - r[4]) * 1e-3;
+            ++cnt;
+        }
+        if (cnt) fprintf(stderr, "[ccqp timing] world %d: pass %.1f  reduce2 %.1f  gemv %.1f  reduce1 %.1f  scalar %.1f  us (mean of %d iterations)\n",
+                         h->world, acc[0] / cnt, acc[1] / cnt, acc[2] / cnt, acc[3] / cnt, acc[4] / cnt, cnt);
+    }
     const DenseOut* o = reinterpret_cast<const DenseOut*>(h->out_host);
     std::memset(result, 0, sizeof(*result));
     result->residual = o->residual;

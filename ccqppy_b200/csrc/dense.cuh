@@ -32,7 +32,6 @@ namespace ccqp {
 constexpr int kDenseThreads = CCQP_DENSE_THREADS;
 constexpr int kDenseWarps = kDenseThreads / 32;
 constexpr int kUnroll = CCQP_UNROLL;  // 256-bit loads in flight per lane
-constexpr int kMaxRed = 8;            // doubles per grid reduction
 constexpr int kMaxWindow = 64;        // SPG non-monotone window
 
 enum DenseOp : int {
@@ -59,10 +58,7 @@ struct DenseCtx {
     const double* x0;   // [npad] (zeros if the caller passed none)
     ProjTable T;
     double* vec[kNumVec];   // work vectors, [npad] each, zero tails
-    double* partials;       // [2][grid][kMaxRed]
-    unsigned long long* andparts;   // [2][grid]
-    unsigned* bar_counter;
-    unsigned* abort_flag;
+    GridSyncCtx gs;         // arrive / go words, partials [2][grid][kMaxRed], results
     const double* uniforms;
     long long n_uniforms;
     double tol, max_mv, step, tau, sig1, sig2;
@@ -79,6 +75,7 @@ struct DenseCtx {
     // test hooks
     const double* hook_in;
     double* hook_out;
+    long long* dbg;     // phase time stamps of CTA 0 (tuning aid, CCQP_DEBUG_TIMING=1); null = off
     // row-sharded multi-GPU solves (world == 1: unused)
     XComm x;
 };
@@ -103,23 +100,24 @@ __host__ __device__ inline size_t dense_smem_bytes(int CW, int rows_max, int nse
 }
 
 struct Kst {                // per-thread kernel state
-    GridSync gs;
-    XSync xs;
+    unsigned epoch, xepoch; // grid_xsync counts (identical in every thread of every CTA of every rank)
     DenseSmem sm;
     int gtid, gstride;
     int r0, r1;             // rows of this CTA (global indices)
     unsigned par[2];        // mbarrier phase parity per buffer
-    int redbuf;             // partial-buffer parity
+    int yq;                 // next buffer of the mat-vec output pool
     long long mv, gemv, iters, draws;
 };
 
 // ------------------------------------------------------------------------------------------
 // reductions across the grid (the barrier also orders all prior global writes)
 // ------------------------------------------------------------------------------------------
-// Barrier between phases.  Single GPU: grid barrier.  Sharded: every rank's grid + all ranks.
+// Barrier between phases: the whole grid, and every rank of a sharded solve (common.cuh grid_xsync).
+// kCross: the sync closes a mat-vec phase, whose output rows other ranks are about to read.
+template <bool kCross>
 __device__ __forceinline__ void barrier_only(Kst& k, const DenseCtx& c) {
-    if (c.x.world > 1) xgpu_barrier(c.x, k.xs, c.abort_flag);
-    else grid_barrier(k.gs);
+    unsigned long long none[1] = {0};
+    grid_xsync<0, false>(c.gs, c.x, k.epoch, k.xepoch, kCross, none, reinterpret_cast<unsigned long long*>(k.sm.scratch));
 }
 
 // store into a vector that a later mat-vec reads in full: the owning rank also writes the entry
@@ -134,101 +132,32 @@ __device__ __forceinline__ void pub_store(const DenseCtx& c, double* vec, int i,
     }
 }
 
-template <int K>
+// Sum of K per-thread values over the grid (and over all ranks), fused with the phase barrier.
+// Order: lanes -> warps -> CTAs (strided over 32 lanes, then a shuffle tree) -> ranks in rank
+// order; fixed for a given launch shape, identical on every rank.
+// kCross = true: the values are partial sums over this rank's ROWS (mat-vec epilogue) and the sync
+// closes the mat-vec phase; kCross = false: every rank summed the full-length vectors itself.
+template <int K, bool kCross>
 __device__ __forceinline__ void reduce_sync(Kst& k, const DenseCtx& c, double (&a)[K]) {
-    static_assert(K <= kMaxRed, "too many reduction slots");
     cta_sum<K>(a, k.sm.scratch);
-    const int G = gridDim.x;
-    double* part = c.partials + (size_t)k.redbuf * G * kMaxRed;
-    if (threadIdx.x == 0) {
+    unsigned long long v[K];
 #pragma unroll
-        for (int j = 0; j < K; ++j) part[(size_t)blockIdx.x * kMaxRed + j] = a[j];
-    }
-    grid_barrier(k.gs);
-    if (threadIdx.x < 32) {
-        const int lane = threadIdx.x;
+    for (int j = 0; j < K; ++j) v[j] = (unsigned long long)__double_as_longlong(a[j]);
+    grid_xsync<K, false>(c.gs, c.x, k.epoch, k.xepoch, kCross, v, reinterpret_cast<unsigned long long*>(k.sm.scratch));
 #pragma unroll
-        for (int j = 0; j < K; ++j) {
-            double s = 0.0;
-            for (int q = lane; q < G; q += 32) s += ld_cg(part + (size_t)q * kMaxRed + j);
-            s = warp_sum(s);
-            if (lane == 0) k.sm.scratch[j] = s;
-        }
-    }
-    __syncthreads();
-    if (c.x.world > 1) {
-        // rank-local sums -> every peer's xpart[buf][rank][:], then all ranks add the world's
-        // contributions in rank order, so every rank holds bit-identical scalars
-        if (blockIdx.x == 0 && threadIdx.x < K) {
-            const double v = k.sm.scratch[threadIdx.x];
-            const size_t off = kSymXpartOff + (((size_t)k.redbuf * kMaxWorld + c.x.rank) * kMaxRed + threadIdx.x) * 8;
-            for (int s = 0; s < c.x.world; ++s) *reinterpret_cast<double*>(c.x.base[s] + off) = v;
-        }
-        xgpu_barrier(c.x, k.xs, c.abort_flag);
-        if (threadIdx.x < K) {
-            const double* xp = reinterpret_cast<const double*>(c.x.base[c.x.rank] + kSymXpartOff) +
-                               (size_t)k.redbuf * kMaxWorld * kMaxRed + threadIdx.x;
-            double s = 0.0;
-            for (int r = 0; r < c.x.world; ++r) s += ld_cg(xp + (size_t)r * kMaxRed);
-            k.sm.scratch[threadIdx.x] = s;
-        }
-        __syncthreads();
-    }
-#pragma unroll
-    for (int j = 0; j < K; ++j) a[j] = k.sm.scratch[j];
-    __syncthreads();
-    k.redbuf ^= 1;
+    for (int j = 0; j < K; ++j) a[j] = __longlong_as_double((long long)v[j]);
 }
 
-// bitwise AND of a 64-bit mask over the grid
+// bitwise AND of a 64-bit mask over the grid (and over all ranks)
 __device__ __forceinline__ unsigned long long and_sync(Kst& k, const DenseCtx& c, unsigned long long m) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     m = warp_and64(m);
     if (lane == 0) k.sm.ascratch[warp] = m;
     __syncthreads();
-    const int G = gridDim.x;
-    unsigned long long* part = c.andparts + (size_t)k.redbuf * G;
-    if (threadIdx.x == 0) {
-        unsigned long long t = ~0ull;
-        for (int w = 0; w < kDenseWarps; ++w) t &= k.sm.ascratch[w];
-        part[blockIdx.x] = t;
-    }
-    grid_barrier(k.gs);
-    if (threadIdx.x < 32) {
-        unsigned long long t = ~0ull;
-        for (int q = lane; q < G; q += 32) {
-            unsigned long long v;
-            asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(v) : "l"(part + q) : "memory");
-            t &= v;
-        }
-        t = warp_and64(t);
-        if (lane == 0) k.sm.ascratch[0] = t;
-    }
-    __syncthreads();
-    if (c.x.world > 1) {
-        if (blockIdx.x == 0 && threadIdx.x == 0) {
-            const unsigned long long v = k.sm.ascratch[0];
-            const size_t off = kSymApartOff + ((size_t)k.redbuf * kMaxWorld + c.x.rank) * 8;
-            for (int s = 0; s < c.x.world; ++s) *reinterpret_cast<unsigned long long*>(c.x.base[s] + off) = v;
-        }
-        xgpu_barrier(c.x, k.xs, c.abort_flag);
-        if (threadIdx.x == 0) {
-            const unsigned long long* ap = reinterpret_cast<const unsigned long long*>(c.x.base[c.x.rank] + kSymApartOff) +
-                                           (size_t)k.redbuf * kMaxWorld;
-            unsigned long long t = ~0ull;
-            for (int r = 0; r < c.x.world; ++r) {
-                unsigned long long v;
-                asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(v) : "l"(ap + r) : "memory");
-                t &= v;
-            }
-            k.sm.ascratch[0] = t;
-        }
-        __syncthreads();
-    }
-    const unsigned long long r = k.sm.ascratch[0];
-    __syncthreads();
-    k.redbuf ^= 1;
-    return r;
+    unsigned long long v[1] = {~0ull};
+    if (threadIdx.x == 0) for (int w = 0; w < kDenseWarps; ++w) v[0] &= k.sm.ascratch[w];
+    grid_xsync<1, true>(c.gs, c.x, k.epoch, k.xepoch, false, v, reinterpret_cast<unsigned long long*>(k.sm.scratch));
+    return v[0];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -344,7 +273,23 @@ __device__ __forceinline__ void gemv_phase(Kst& k, const DenseCtx& c, const doub
 // ------------------------------------------------------------------------------------------
 // small helpers for the solver programs
 // ------------------------------------------------------------------------------------------
-#define CCQP_ELEMS(i) for (int i = c.T.e0 + k.gtid; i < c.T.e1; i += k.gstride)
+// Sharded solves ("replicated vectors, sharded matrix").  Every rank keeps ALL vectors in full and
+// repeats the (tiny) elementwise work; only the mat-vec is split by rows.  The rows a rank computes
+// are written into every peer's copy of the output vector from inside the mat-vec epilogue
+// (pub_store: the all-gather, fused), and the sync that closes the mat-vec phase is the only
+// cross-GPU sync of an iteration (it also carries the row-local partial sums: the all-reduce).
+// Mat-vec outputs land in a rotating pool of three buffers: a fast rank may already be writing the
+// output of phase q+1 into a slow rank's memory while that rank still reads the output of phase q
+// (or q-1, e.g. BBPGD's previous gradient), so a buffer is reused only every third output; values
+// that must live longer are copied to a rank-local vector by the elementwise pass that reads them.
+#define CCQP_ELEMS(i) for (int i = k.gtid; i < c.n; i += k.gstride)
+
+constexpr int kPool = 3;                    // vec[kNumVec - 3 ..] are the mat-vec output pool
+__device__ __forceinline__ double* next_y(Kst& k, const DenseCtx& c) {
+    double* y = c.vec[kNumVec - kPool + k.yq];
+    k.yq = (k.yq + 1 == kPool) ? 0 : k.yq + 1;
+    return y;
+}
 
 __device__ __forceinline__ void swap_ptr(double*& a, double*& b) { double* t = a; a = b; b = t; }
 
@@ -360,7 +305,7 @@ __device__ __forceinline__ double residual_partial(Kst& k, const DenseCtx& c, do
 }
 
 __device__ __forceinline__ void finish(Kst& k, const DenseCtx& c, const double* xsol, double res, int status) {
-    CCQP_ELEMS(i) pub_store(c, c.x_out, i, ld_cg(xsol + i));   // every rank returns the full solution
+    CCQP_ELEMS(i) c.x_out[i] = ld_cg(xsol + i);   // every rank holds the full solution
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         DenseOut o;
         o.residual = res;
@@ -369,7 +314,15 @@ __device__ __forceinline__ void finish(Kst& k, const DenseCtx& c, const double* 
         o.status = status;
         *c.out = o;
     }
-    if (c.x.world > 1) xgpu_barrier(c.x, k.xs, c.abort_flag);   // peers' slices of x_out have landed
+}
+
+constexpr int kDbgSlots = 8, kDbgIters = 64;
+__device__ __forceinline__ void dbg_stamp(const DenseCtx& c, long long it, int slot) {
+    if (c.dbg && blockIdx.x == 0 && threadIdx.x == 0 && it < kDbgIters) {
+        long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        c.dbg[it * kDbgSlots + slot] = t;
+    }
 }
 
 __device__ __forceinline__ bool hit_max(const Kst& k, const DenseCtx& c) { return (double)k.mv >= c.max_mv; }
@@ -379,17 +332,17 @@ __device__ __forceinline__ bool hit_max(const Kst& k, const DenseCtx& c) { retur
 // ------------------------------------------------------------------------------------------
 template <int MODE>
 __device__ void solve_pgd_family(Kst& k, const DenseCtx& c) {
-    double *x = c.vec[0], *xm = c.vec[1], *g = c.vec[2], *gm = c.vec[3];
-    double *xmin = c.vec[4], *gmin = c.vec[5];
+    double *x = c.vec[0], *xm = c.vec[1], *xmin = c.vec[2], *gmin = c.vec[3];
     const double cs = 1.0 / (3 * (double)c.n * kGd);
     const double* b = c.b;
-    CCQP_ELEMS(i) { const double v = c.x0[i]; x[i] = v; pub_store(c, xm, i, v); if (MODE == OP_BBPGDF) { xmin[i] = v; gmin[i] = v; } }
-    barrier_only(k, c);
-    gemv_phase(k, c, xm, [&](int r, double s) { pub_store(c, gm, r, s + b[r]); });   // gm feeds A gm below
+    CCQP_ELEMS(i) { const double v = c.x0[i]; x[i] = v; xm[i] = v; if (MODE == OP_BBPGDF) { xmin[i] = v; gmin[i] = v; } }
+    barrier_only<false>(k, c);
+    double* gm = next_y(k, c);
+    gemv_phase(k, c, xm, [&](int r, double s) { pub_store(c, gm, r, s + b[r]); });
     k.mv = 1;
-    barrier_only(k, c);
+    barrier_only<true>(k, c);
     double a1[1] = {residual_partial(k, c, cs, [&](int i) { return ld_cg(xm + i); }, [&](int i) { return ld_cg(gm + i); })};
-    reduce_sync<1>(k, c, a1);
+    reduce_sync<1, false>(k, c, a1);
     double res = sqrt(a1[0]);
     double resmin = INFINITY;
     const double* xsol = x;
@@ -398,17 +351,18 @@ __device__ void solve_pgd_family(Kst& k, const DenseCtx& c) {
         if (MODE != OP_PGD) {   // alpha0 = g.g / g.Ag, product not counted (:635, :775)
             double a2[2] = {0.0, 0.0};
             gemv_phase(k, c, gm, [&](int r, double s) { const double gr = ld_cg(gm + r); a2[0] = fma(gr, s, a2[0]); a2[1] = fma(gr, gr, a2[1]); });
-            reduce_sync<2>(k, c, a2);
+            reduce_sync<2, true>(k, c, a2);
             step = a2[1] / a2[0];
         }
         for (;;) {
             project_pass(c.T, k.gtid, k.gstride, k.sm.scratch,
                          [&](int i) { return ld_cg(xm + i) - step * ld_cg(gm + i); },
-                         [&](int i, double, double p) { pub_store(c, x, i, p); });
-            barrier_only(k, c);
-            gemv_phase(k, c, x, [&](int r, double s) { g[r] = s + b[r]; });
+                         [&](int i, double, double p) { x[i] = p; });
+            barrier_only<false>(k, c);
+            double* g = next_y(k, c);
+            gemv_phase(k, c, x, [&](int r, double s) { pub_store(c, g, r, s + b[r]); });
             k.mv += 1;
-            barrier_only(k, c);
+            barrier_only<true>(k, c);
             xsol = x;
             if (hit_max(k, c)) break;
             double a3[3] = {0.0, 0.0, 0.0};
@@ -424,7 +378,7 @@ __device__ void solve_pgd_family(Kst& k, const DenseCtx& c) {
                                  a3[2] = fma(s, y, a3[2]);
                              }
                          });
-            reduce_sync<3>(k, c, a3);
+            reduce_sync<3, false>(k, c, a3);
             res = sqrt(a3[0]);
             k.iters += 1;
             if (res < c.tol) break;
@@ -434,27 +388,27 @@ __device__ void solve_pgd_family(Kst& k, const DenseCtx& c) {
                     CCQP_ELEMS(i) { xmin[i] = ld_cg(x + i); gmin[i] = ld_cg(g + i); }
                 }
                 if (step < 10 * kEps) {   // stagnation: x replaced (g is not), BB sums redone
-                    barrier_only(k, c);
+                    barrier_only<false>(k, c);
                     project_pass(c.T, k.gtid, k.gstride, k.sm.scratch,
                                  [&](int i) { return ld_cg(xmin + i) - kGd * ld_cg(gmin + i); },
-                                 [&](int i, double, double p) { pub_store(c, x, i, p); });
-                    barrier_only(k, c);
+                                 [&](int i, double, double p) { x[i] = p; });
+                    barrier_only<false>(k, c);
                     double a2[2] = {0.0, 0.0};
                     CCQP_ELEMS(i) {
                         const double s = ld_cg(x + i) - ld_cg(xm + i), y = ld_cg(g + i) - ld_cg(gm + i);
                         a2[0] = fma(s, s, a2[0]);
                         a2[1] = fma(s, y, a2[1]);
                     }
-                    reduce_sync<2>(k, c, a2);
+                    reduce_sync<2, false>(k, c, a2);
                     a3[1] = a2[0]; a3[2] = a2[1];
                 }
             }
             if (MODE != OP_PGD) step = a3[1] / (a3[2] + 10 * kEps);
             swap_ptr(x, xm);
-            swap_ptr(g, gm);
+            gm = g;
         }
     }
-    barrier_only(k, c);
+    barrier_only<false>(k, c);
     finish(k, c, xsol, res, 0);
 }
 
@@ -462,23 +416,25 @@ __device__ void solve_pgd_family(Kst& k, const DenseCtx& c) {
 // SPG-QP                                                           solvers.py:906-975
 // ------------------------------------------------------------------------------------------
 __device__ void solve_spg(Kst& k, const DenseCtx& c) {
-    double *x = c.vec[0], *g = c.vec[1], *d = c.vec[2], *Ad = c.vec[3];
+    double *x = c.vec[0], *g = c.vec[1], *d = c.vec[2];
     const double* b = c.b;
-    CCQP_ELEMS(i) pub_store(c, x, i, c.x0[i]);
-    barrier_only(k, c);
+    CCQP_ELEMS(i) x[i] = c.x0[i];
+    barrier_only<false>(k, c);
     double a2[2] = {0.0, 0.0};
+    double* g0 = next_y(k, c);
     gemv_phase(k, c, x, [&](int r, double s) {
         const double gr = s + b[r];
-        pub_store(c, g, r, gr);                  // g feeds A g below
+        pub_store(c, g0, r, gr);
         a2[0] = fma(gr, ld_cg(x + r), a2[0]);   // f0 = g.x (:923, kept as written)
         a2[1] = fma(gr, gr, a2[1]);
     });
-    reduce_sync<2>(k, c, a2);
+    reduce_sync<2, true>(k, c, a2);
     double f = a2[0];
     const double gg = a2[1];
+    CCQP_ELEMS(i) g[i] = ld_cg(g0 + i);         // g lives for the whole solve: rank-local copy
     double a1[1] = {0.0};
-    gemv_phase(k, c, g, [&](int r, double s) { a1[0] = fma(ld_cg(g + r), s, a1[0]); });
-    reduce_sync<1>(k, c, a1);
+    gemv_phase(k, c, g0, [&](int r, double s) { a1[0] = fma(ld_cg(g0 + r), s, a1[0]); });
+    reduce_sync<1, true>(k, c, a1);
     double alpha = gg / a1[0];
     k.mv = 2;
     double window[kMaxWindow];
@@ -486,8 +442,10 @@ __device__ void solve_spg(Kst& k, const DenseCtx& c) {
     window[0] = f;
     double dd_rep = NAN;                 // residual reported = sqrt(d.d) of the last completed test
     double bk = 0.0;                     // pending update x += bk d, g += bk Ad (applied lazily)
+    const double* Ad = c.vec[3];         // all zeros; multiplied by bk == 0 in the first pass
     int status = 0;
     for (;;) {
+        dbg_stamp(c, k.iters, 0);
         double s2[2] = {0.0, 0.0};       // d.d, d.g
         project_pass(c.T, k.gtid, k.gstride, k.sm.scratch,
                      [&](int i) {
@@ -500,17 +458,22 @@ __device__ void solve_spg(Kst& k, const DenseCtx& c) {
                          const double xi = fma(bk, ld_cg(d + i), ld_cg(x + i));
                          const double gi = fma(bk, ld_cg(Ad + i), ld_cg(g + i));
                          const double di = p - xi;
-                         x[i] = xi; g[i] = gi;
-                         pub_store(c, d, i, di);
+                         x[i] = xi; g[i] = gi; d[i] = di;
                          s2[0] = fma(di, di, s2[0]);
                          s2[1] = fma(di, gi, s2[1]);
                      });
         bk = 0.0;
-        reduce_sync<2>(k, c, s2);
+        dbg_stamp(c, k.iters, 1);
+        reduce_sync<2, false>(k, c, s2);
+        dbg_stamp(c, k.iters, 2);
         double s1[1] = {0.0};
-        gemv_phase(k, c, d, [&](int r, double s) { Ad[r] = s; s1[0] = fma(ld_cg(d + r), s, s1[0]); });
+        double* Adn = next_y(k, c);
+        gemv_phase(k, c, d, [&](int r, double s) { pub_store(c, Adn, r, s); s1[0] = fma(ld_cg(d + r), s, s1[0]); });
+        Ad = Adn;
         k.mv += 1;
-        reduce_sync<1>(k, c, s1);
+        dbg_stamp(c, k.iters, 3);
+        reduce_sync<1, true>(k, c, s1);
+        dbg_stamp(c, k.iters, 4);
         if (hit_max(k, c)) break;
         const double dd = s2[0], dg = s2[1], dAd = s1[0];
         dd_rep = dd;
@@ -533,7 +496,7 @@ __device__ void solve_spg(Kst& k, const DenseCtx& c) {
         alpha = dd / dAd;
         k.iters += 1;
     }
-    barrier_only(k, c);
+    barrier_only<false>(k, c);
     finish(k, c, x, sqrt(dd_rep), status);
 }
 
@@ -542,57 +505,61 @@ __device__ void solve_spg(Kst& k, const DenseCtx& c) {
 // ------------------------------------------------------------------------------------------
 template <bool AR>
 __device__ void solve_apgd(Kst& k, const DenseCtx& c) {
-    double *x = c.vec[0], *xp = c.vec[1], *y = c.vec[2], *yn = c.vec[3], *g = c.vec[4], *Axp = c.vec[5];
-    double *xhat = c.vec[6], *v0 = c.vec[7];
+    double *x = c.vec[0], *xp = c.vec[1], *y = c.vec[2], *yn = c.vec[3], *g = c.vec[4];
+    double *xhat = c.vec[5], *v0 = c.vec[6];
     const double* b = c.b;
     const double cs = 1.0 / (3 * (double)c.n * kGd);
     double a1[1] = {0.0};
     CCQP_ELEMS(i) {
         const double v = c.x0[i];
-        x[i] = v; xp[i] = v;
-        pub_store(c, y, i, v);
+        x[i] = v; xp[i] = v; y[i] = v;
         if (AR) xhat[i] = 1.0;
         const double dv = v - 1.0;
-        pub_store(c, v0, i, dv);
+        v0[i] = dv;
         a1[0] = fma(dv, dv, a1[0]);
     }
-    reduce_sync<1>(k, c, a1);
+    reduce_sync<1, false>(k, c, a1);
     const double dn2 = a1[0];
     a1[0] = 0.0;
     gemv_phase(k, c, v0, [&](int, double s) { a1[0] = fma(s, s, a1[0]); });
-    reduce_sync<1>(k, c, a1);
+    reduce_sync<1, true>(k, c, a1);
     double L = sqrt(a1[0]) / sqrt(dn2);
     double t = 1.0 / L;
     k.mv = 1;
     double theta = 1.0, res = NAN, resmin = INFINITY;
+    const double* Axp = v0;              // set by the first inner mat-vec
     for (;;) {
         double r12[2] = {0.0, 0.0};
+        double* gy = next_y(k, c);
         gemv_phase(k, c, y, [&](int r, double s) {
             const double yr = ld_cg(y + r), br = b[r];
-            g[r] = s + br;
+            pub_store(c, gy, r, s + br);
             r12[0] = fma(yr, s, r12[0]);
             r12[1] = fma(yr, br, r12[1]);
         });
         k.mv += 1;
-        reduce_sync<2>(k, c, r12);
+        reduce_sync<2, true>(k, c, r12);
         if (hit_max(k, c)) break;
         const double rt1 = r12[0] * 0.5, rt2 = r12[1];
+        // g is read again by the backtracking steps and the restart test: rank-local copy
         project_pass(c.T, k.gtid, k.gstride, k.sm.scratch,
-                     [&](int i) { return ld_cg(y + i) - t * ld_cg(g + i); },
-                     [&](int i, double, double p) { pub_store(c, xp, i, p); });
-        barrier_only(k, c);
+                     [&](int i) { return ld_cg(y + i) - t * ld_cg(gy + i); },
+                     [&](int i, double, double p) { g[i] = ld_cg(gy + i); xp[i] = p; });
+        barrier_only<false>(k, c);
         for (;;) {   // Lipschitz backtracking :288-310
             double q[4] = {0.0, 0.0, 0.0, 0.0};
+            double* ax = next_y(k, c);
             gemv_phase(k, c, xp, [&](int r, double s) {
-                Axp[r] = s;
+                pub_store(c, ax, r, s);
                 const double xr = ld_cg(xp + r), df = xr - ld_cg(y + r);
                 q[0] = fma(xr, s, q[0]);
                 q[1] = fma(xr, b[r], q[1]);
                 q[2] = fma(ld_cg(g + r), df, q[2]);
                 q[3] = fma(df, df, q[3]);
             });
+            Axp = ax;
             k.mv += 1;
-            reduce_sync<4>(k, c, q);
+            reduce_sync<4, true>(k, c, q);
             if (hit_max(k, c)) break;   // leaves the inner loop only (:292-293)
             const double lt1 = q[0] * 0.5, lt2 = q[1], rt3 = q[2], rt4 = 0.5 * L * q[3];
             if ((lt1 + lt2) <= (rt1 + rt2 + rt3 + rt4)) break;
@@ -600,8 +567,8 @@ __device__ void solve_apgd(Kst& k, const DenseCtx& c) {
             t = 1.0 / L;
             project_pass(c.T, k.gtid, k.gstride, k.sm.scratch,
                          [&](int i) { return ld_cg(y + i) - t * ld_cg(g + i); },
-                         [&](int i, double, double p) { pub_store(c, xp, i, p); });
-            barrier_only(k, c);
+                         [&](int i, double, double p) { xp[i] = p; });
+            barrier_only<false>(k, c);
         }
         double theta_n = 0.5 * (-theta * theta + theta * sqrt(4 + theta * theta));
         const double beta = theta * (1 - theta) / (theta * theta + theta_n);
@@ -613,9 +580,9 @@ __device__ void solve_apgd(Kst& k, const DenseCtx& c) {
                          const double dr = cs * (xpi - p);
                          r2[0] = fma(dr, dr, r2[0]);
                          if (AR) r2[1] = fma(ld_cg(g + i), xpi - xi, r2[1]);
-                         pub_store(c, yn, i, (1 + beta) * xpi - beta * xi);
+                         yn[i] = (1 + beta) * xpi - beta * xi;
                      });
-        reduce_sync<2>(k, c, r2);
+        reduce_sync<2, false>(k, c, r2);
         res = sqrt(r2[0]);
         k.iters += 1;
         if (AR && res < resmin) {
@@ -624,9 +591,9 @@ __device__ void solve_apgd(Kst& k, const DenseCtx& c) {
         }
         if (res < c.tol) break;
         if (AR && r2[1] > 0) {   // :510-512
-            CCQP_ELEMS(i) pub_store(c, yn, i, ld_cg(xp + i));
+            CCQP_ELEMS(i) yn[i] = ld_cg(xp + i);
             theta_n = 1;
-            barrier_only(k, c);
+            barrier_only<false>(k, c);
         }
         L *= 0.9;
         t = 1.0 / L;
@@ -634,7 +601,7 @@ __device__ void solve_apgd(Kst& k, const DenseCtx& c) {
         swap_ptr(x, xp);   // afterwards xp names the previous x (what :336 returns on the mv limit)
         theta = theta_n;
     }
-    barrier_only(k, c);
+    barrier_only<false>(k, c);
     finish(k, c, AR ? xhat : xp, res, 0);
 }
 
@@ -670,6 +637,20 @@ __device__ unsigned long long bisect_mask(Kst& k, const DenseCtx& c, const doubl
     return and_sync(k, c, m);
 }
 
+// y = epi(r, (A vin)_r) for this rank's rows, complete in `dst` on every rank when the call
+// returns.  Sharded solves go through the output pool and copy (see the top of this section);
+// a single GPU writes dst directly.  Ends with a barrier.
+template <class Epi>
+__device__ __forceinline__ void gemv_into(Kst& k, const DenseCtx& c, const double* vin, double* dst, Epi epi) {
+    double* y = (c.x.world > 1) ? next_y(k, c) : dst;
+    gemv_phase(k, c, vin, [&](int r, double s) { pub_store(c, y, r, epi(r, s)); });
+    barrier_only<true>(k, c);
+    if (y != dst) {
+        CCQP_ELEMS(i) dst[i] = ld_cg(y + i);
+        barrier_only<false>(k, c);
+    }
+}
+
 __device__ void solve_mprgp(Kst& k, const DenseCtx& c) {
     double *xk = c.vec[0], *xn = c.vec[1], *gk = c.vec[2], *gn = c.vec[3], *p = c.vec[4], *Ap = c.vec[5];
     double *nv = c.vec[6], *w = c.vec[7], *dl = c.vec[8];
@@ -677,28 +658,27 @@ __device__ void solve_mprgp(Kst& k, const DenseCtx& c) {
     const double cs = 1.0 / (3 * (double)c.n * kGd);
     int status = 0;
     project_pass(c.T, k.gtid, k.gstride, k.sm.scratch, [&](int i) { return c.x0[i]; },
-                 [&](int i, double, double pr) { pub_store(c, xk, i, pr); xn[i] = pr; });
-    barrier_only(k, c);
-    gemv_phase(k, c, xk, [&](int r, double s) { const double v = s + b[r]; pub_store(c, gk, r, v); gn[r] = v; });
+                 [&](int i, double, double pr) { xk[i] = pr; xn[i] = pr; });
+    barrier_only<false>(k, c);
+    gemv_into(k, c, xk, gk, [&](int r, double s) { return s + b[r]; });
     k.mv = 1;
-    barrier_only(k, c);
+    CCQP_ELEMS(i) gn[i] = ld_cg(gk + i);
     double a1[1] = {residual_partial(k, c, cs, [&](int i) { return ld_cg(xk + i); }, [&](int i) { return ld_cg(gk + i); })};
-    reduce_sync<1>(k, c, a1);
+    reduce_sync<1, false>(k, c, a1);
     double res = sqrt(a1[0]);
     if (res >= c.tol) {
         double a2[2] = {0.0, 0.0};
         gemv_phase(k, c, gk, [&](int r, double s) { const double gr = ld_cg(gk + r); a2[0] = fma(gr, s, a2[0]); a2[1] = fma(gr, gr, a2[1]); });
         k.mv += 1;                                   // counted (:1077-1078)
-        reduce_sync<2>(k, c, a2);
+        reduce_sync<2, true>(k, c, a2);
         double abb = a2[1] / a2[0];
         bool abb_lazy = false;                       // true: abb = BB(xk - xn) still to be evaluated
         project_pass(c.T, k.gtid, k.gstride, k.sm.scratch, [&](int i) { return ld_cg(xk + i); },
-                     [&](int i, double t, double pr) { pub_store(c, p, i, is_close(t, pr) ? ld_cg(gk + i) : 0.0); });
-        barrier_only(k, c);
+                     [&](int i, double t, double pr) { p[i] = is_close(t, pr) ? ld_cg(gk + i) : 0.0; });
+        barrier_only<false>(k, c);
         for (;;) {
-            gemv_phase(k, c, xk, [&](int r, double s) { gk[r] = s + b[r]; });
+            gemv_into(k, c, xk, gk, [&](int r, double s) { return s + b[r]; });
             k.mv += 1;
-            barrier_only(k, c);
             if (hit_max(k, c)) break;
             // delta = isclose(xk, P(xk)); psi = delta*gk   (:1093-1094)
             double q3[3] = {0.0, 0.0, 0.0};          // psi.psi, psi.p, #(!delta)
@@ -711,31 +691,38 @@ __device__ void solve_mprgp(Kst& k, const DenseCtx& c) {
                              if (!cl) q3[2] += 1.0;
                              dl[i] = cl ? 1.0 : 0.0;
                          });
-            reduce_sync<3>(k, c, q3);
+            reduce_sync<3, false>(k, c, q3);
             if (c.T.has_cone_ref) { status = 6; break; }   // normal_vector raises (:1095, ss:465)
             double betbet = 0.0;
             if (q3[2] > 0.0) {
                 // rare: some entries of xk are not (close to) feasible; the chopped gradient
                 // needs normal_vector(xk) and the GLOBAL n.g (:1095-1097)
                 normal_pass(c.T, k.gtid, k.gstride, k.sm.scratch, [&](int i) { return ld_cg(xk + i); }, nv);
-                barrier_only(k, c);
+                barrier_only<false>(k, c);
                 double s1[1] = {0.0};
                 CCQP_ELEMS(i) s1[0] = fma(ld_cg(nv + i), ld_cg(gk + i), s1[0]);
-                reduce_sync<1>(k, c, s1);
+                reduce_sync<1, false>(k, c, s1);
                 const double mng = s1[0] < 0.0 ? s1[0] : 0.0;    // np.min([0, n.g])
                 double s2[1] = {0.0};
                 CCQP_ELEMS(i) {
                     const double bv = (1.0 - ld_cg(dl + i)) * (ld_cg(gk + i) - mng * ld_cg(nv + i));
                     s2[0] = fma(bv, bv, s2[0]);
                 }
-                reduce_sync<1>(k, c, s2);
+                reduce_sync<1, false>(k, c, s2);
                 betbet = s2[0];
             }
             if (betbet < q3[0]) {
                 double s1[1] = {0.0};
-                gemv_phase(k, c, p, [&](int r, double s) { Ap[r] = s; s1[0] = fma(ld_cg(p + r), s, s1[0]); });
-                k.mv += 1;
-                reduce_sync<1>(k, c, s1);
+                {
+                    double* y = (c.x.world > 1) ? next_y(k, c) : Ap;
+                    gemv_phase(k, c, p, [&](int r, double s) { pub_store(c, y, r, s); s1[0] = fma(ld_cg(p + r), s, s1[0]); });
+                    k.mv += 1;
+                    reduce_sync<1, true>(k, c, s1);
+                    if (y != Ap) {
+                        CCQP_ELEMS(i) Ap[i] = ld_cg(y + i);
+                        barrier_only<false>(k, c);
+                    }
+                }
                 if (hit_max(k, c)) break;
                 const double pAp = s1[0];
                 const double acg = q3[1] / pAp;
@@ -753,13 +740,14 @@ __device__ void solve_mprgp(Kst& k, const DenseCtx& c) {
                                  [&](int i, double yv, double pr) {
                                      const double api = ld_cg(Ap + i);
                                      const double gni = ld_cg(gk + i) - acg * api;
-                                     pub_store(c, xn, i, yv);
+                                     xn[i] = yv;
                                      gn[i] = gni;
                                      const double psy = is_close(yv, pr) ? gni : 0.0;
                                      const double bet = psy * api / pAp;          // elementwise "beta" (:1134)
-                                     pub_store(c, p, i, psy - bet * ld_cg(p + i));
+                                     p[i] = psy - bet * ld_cg(p + i);
                                  });
-                    abb_lazy = true;   // same element->thread map as the residual pass: no barrier
+                    abb_lazy = true;
+                    barrier_only<false>(k, c);
                 } else {
                     // expansion step with a BB step length :1136-1163
                     double s2[2] = {0.0, 0.0};
@@ -770,7 +758,7 @@ __device__ void solve_mprgp(Kst& k, const DenseCtx& c) {
                         s2[0] = fma(sx, sx, s2[0]);
                         s2[1] = fma(sx, sg, s2[1]);
                     }
-                    reduce_sync<2>(k, c, s2);
+                    reduce_sync<2, false>(k, c, s2);
                     const double a = s2[0] / (s2[1] + 10 * kEps);
                     project_pass(c.T, k.gtid, k.gstride, k.sm.scratch,
                                  [&](int i) {
@@ -778,39 +766,40 @@ __device__ void solve_mprgp(Kst& k, const DenseCtx& c) {
                                      const double gh = ld_cg(gk + i) - af * ld_cg(Ap + i);
                                      return xh - a * gh;
                                  },
-                                 [&](int i, double, double pr) { pub_store(c, xn, i, pr); });
-                    barrier_only(k, c);
-                    gemv_phase(k, c, xn, [&](int r, double s) { gn[r] = s + b[r]; });
+                                 [&](int i, double, double pr) { xn[i] = pr; });
+                    barrier_only<false>(k, c);
+                    gemv_into(k, c, xn, gn, [&](int r, double s) { return s + b[r]; });
                     k.mv += 1;
-                    barrier_only(k, c);
                     if (hit_max(k, c)) break;
                     project_pass(c.T, k.gtid, k.gstride, k.sm.scratch, [&](int i) { return ld_cg(xn + i); },
-                                 [&](int i, double t, double pr) { pub_store(c, p, i, is_close(t, pr) ? ld_cg(gn + i) : 0.0); });
+                                 [&](int i, double t, double pr) { p[i] = is_close(t, pr) ? ld_cg(gn + i) : 0.0; });
                     abb_lazy = true;
+                    barrier_only<false>(k, c);
                 }
             } else {
                 // proportioning step :1164-1182
                 if (abb_lazy) {   // alpha_bb of the previous iteration, evaluated only when needed
                     double s1[1] = {0.0};
-                    CCQP_ELEMS(i) { const double dv = ld_cg(xk + i) - ld_cg(xn + i); pub_store(c, w, i, dv); s1[0] = fma(dv, dv, s1[0]); }
-                    reduce_sync<1>(k, c, s1);
+                    CCQP_ELEMS(i) { const double dv = ld_cg(xk + i) - ld_cg(xn + i); w[i] = dv; s1[0] = fma(dv, dv, s1[0]); }
+                    reduce_sync<1, false>(k, c, s1);
                     double s2[1] = {0.0};
                     gemv_phase(k, c, w, [&](int r, double s) { s2[0] = fma(ld_cg(w + r), s, s2[0]); });
-                    reduce_sync<1>(k, c, s2);
+                    reduce_sync<1, true>(k, c, s2);
                     abb = s1[0] / (s2[0] + 10 * kEps);
                 }
                 project_pass(c.T, k.gtid, k.gstride, k.sm.scratch,
                              [&](int i) { return ld_cg(xk + i) - abb * ld_cg(gk + i); },
-                             [&](int i, double, double pr) { pub_store(c, xn, i, pr); });
+                             [&](int i, double, double pr) { xn[i] = pr; });
                 abb_lazy = true;
                 k.mv += 1;            // gk = A xk + b is re-evaluated by the reference (:1174); same value
-                barrier_only(k, c);
+                barrier_only<false>(k, c);
                 if (hit_max(k, c)) break;
                 project_pass(c.T, k.gtid, k.gstride, k.sm.scratch, [&](int i) { return ld_cg(xn + i); },
-                             [&](int i, double t, double pr) { pub_store(c, p, i, is_close(t, pr) ? ld_cg(gn + i) : 0.0); });   // stale gn (:1181)
+                             [&](int i, double t, double pr) { p[i] = is_close(t, pr) ? ld_cg(gn + i) : 0.0; });   // stale gn (:1181)
+                barrier_only<false>(k, c);
             }
             double r1[1] = {residual_partial(k, c, cs, [&](int i) { return ld_cg(xn + i); }, [&](int i) { return ld_cg(gn + i); })};
-            reduce_sync<1>(k, c, r1);
+            reduce_sync<1, false>(k, c, r1);
             res = sqrt(r1[0]);
             k.iters += 1;
             if (res < c.tol) break;
@@ -818,7 +807,7 @@ __device__ void solve_mprgp(Kst& k, const DenseCtx& c) {
             swap_ptr(gk, gn);
         }
     }
-    barrier_only(k, c);
+    barrier_only<false>(k, c);
     finish(k, c, xn, res, status);
 }
 
@@ -838,18 +827,15 @@ __global__ void __launch_bounds__(kDenseThreads, 1) dense_kernel(const DenseCtx 
         k.sm.ascratch = reinterpret_cast<unsigned long long*>(q); q += 32 * 8;
         k.sm.mbar = reinterpret_cast<uint64_t*>(q);
     }
-    k.gs.counter = c.bar_counter;
-    k.gs.abort = c.abort_flag;
-    k.gs.target = 0;
-    k.xs.epoch = 0;
-    k.xs.arrive_target = 0;
+    k.epoch = 0;
+    k.xepoch = 0;
     k.gtid = blockIdx.x * kDenseThreads + threadIdx.x;
     k.gstride = gridDim.x * kDenseThreads;
     k.r0 = c.row0 + (int)(((long long)c.nrows * blockIdx.x) / gridDim.x);
     k.r1 = c.row0 + (int)(((long long)c.nrows * (blockIdx.x + 1)) / gridDim.x);
     k.par[0] = k.par[1] = 0u;
-    k.redbuf = 0;
     k.mv = k.gemv = k.iters = k.draws = 0;
+    k.yq = 0;
     if (threadIdx.x == 0) {
         mbar_init(&k.sm.mbar[0], 1);
         mbar_init(&k.sm.mbar[1], 1);

@@ -99,6 +99,28 @@ class ShardedSolver:
             self._alld = ctypes.create_string_buffer(alld, len(alld))
             _capi.check(self.h.h, lib.ccqp_comm_attach(self.h.h, self._alld))
 
+    def set_matrix(self, shard):
+        """Replace this rank's rows of A.  `shard` is [r1 - r0, n]: a CUDA tensor (borrowed in place) or a
+        host array / CPU tensor (copied to the device by the library; pinned memory makes the copy
+        asynchronous).  Every rank must call it before the next solve()."""
+        import torch
+        r0, r1 = self.ranges[self.rank]
+        if tuple(shard.shape) != (r1 - r0, self.n):
+            raise ValueError("shard must be %s" % ((r1 - r0, self.n),))
+        lib = self.h.lib
+        if hasattr(shard, "is_cuda") and shard.is_cuda:
+            self.shard = shard.to(dtype=torch.float64).contiguous()
+            ptr, lda, mem = self.shard.data_ptr(), self.shard.stride(0), _capi.MEM_DEVICE
+        else:
+            if hasattr(shard, "numpy"):
+                self.shard = shard.to(dtype=torch.float64).contiguous()
+                ptr, lda = self.shard.data_ptr(), self.shard.stride(0)
+            else:
+                self.shard = np.ascontiguousarray(shard, dtype=np.float64)
+                ptr, lda = self.shard.ctypes.data, self.n
+            mem = _capi.MEM_HOST
+        _capi.check(self.h.h, lib.ccqp_set_matrix(self.h.h, ctypes.c_void_p(ptr), self.n, lda, r0, r1 - r0, mem))
+
     def _to_dev(self, v):
         import torch
         if hasattr(v, "is_cuda"):
