@@ -23,7 +23,7 @@ ERR_RANGE = 8
 EXPORTS = ["ccqp_abi_version", "ccqp_status_string", "ccqp_last_error", "ccqp_create", "ccqp_destroy",
            "ccqp_set_stream", "ccqp_get_info", "ccqp_set_matrix", "ccqp_set_projection", "ccqp_solve",
            "ccqp_solve_batched", "ccqp_gemv", "ccqp_gemv_timed", "ccqp_project", "ccqp_normal", "ccqp_comm_export",
-           "ccqp_comm_attach", "ccqp_comm_prepare", "ccqp_comm_detach"]
+           "ccqp_comm_attach", "ccqp_comm_prepare", "ccqp_comm_detach", "ccqp_debug_divide"]
 
 
 class Block(C.Structure):
@@ -81,6 +81,7 @@ def load():
     lib.ccqp_gemv_timed.argtypes = [vp, dp, dp, i32, C.POINTER(C.c_double)]
     lib.ccqp_project.argtypes = [vp, dp, dp, i32]
     lib.ccqp_normal.argtypes = [vp, dp, dp, i32]
+    lib.ccqp_debug_divide.argtypes = [vp, dp, dp, dp, dp, dp, dp, dp, i64]
     lib.ccqp_comm_export.argtypes = [vp, i32, i32, i64, vp]
     lib.ccqp_comm_attach.argtypes = [vp, vp]
     lib.ccqp_comm_prepare.argtypes = [vp]

@@ -44,6 +44,9 @@
 #include "common.cuh"
 #include "../../include/ccqp_b200.h"
 
+#ifndef CCQP_BATCHED_STAGE
+#define CCQP_BATCHED_STAGE 1    // 1: A reaches the registers through a TMA-filled shared tile (next problem in flight
+#endif                          //    during the solve); 0: straight from L2 (bulk L2 prefetch of the next problem)
 #ifndef CCQP_BATCHED_ROWS
 #define CCQP_BATCHED_ROWS 8     // 8: 8x8 sub-blocks (3-stage exchange), 4: 4x16 sub-blocks (2-stage exchange)
 #endif
@@ -79,6 +82,7 @@ struct BatchedCtx {
     BatchedOut* out;        // [batch]
     unsigned* counter;      // work queue head
     int batch, n;
+    int tma_ok;             // rows of A can be moved with 16-byte bulk copies (8n % 16 == 0, 16-byte aligned base)
     int vec_ok;             // rows of A can be read with 256-bit loads (n % 4 == 0, 32-byte aligned base)
     int pf_ok;              // whole problems can be bulk-prefetched into L2 (16-byte granularity)
     double tol, max_mv, step, tau, sig1, sig2;
@@ -88,9 +92,16 @@ struct BatchedCtx {
     int m;
 };
 
+constexpr int kBPitch = kBN + 2;        // tile row pitch (doubles): 528 bytes, conflict-free LDS.128 register fill
 struct BatchedSmem {
-    double xs[2][kBXs];     // mat-vec input, double buffered; 16-entry slices padded by 16 bytes
+#if CCQP_BATCHED_STAGE
+    double tile[kBN * kBPitch];   // the NEXT problem's A, landed by TMA while the current one iterates
+#endif
+    double xs[2][kBXs];     // mat-vec input, double buffered; slices padded by 16 bytes (16-byte aligned)
     double red[2][2][4];    // [parity][warp][slot]
+#if CCQP_BATCHED_STAGE
+    uint64_t mbar;
+#endif
     int next;
 };
 
@@ -343,8 +354,8 @@ __device__ __forceinline__ void solve_one(const BatchedCtx& c, const double (&a)
             dd_rep = dd;
             if (dd <= c.thr_le) break;                                // sqrt(dd) <= tol (:949)
             const double fmax = win.max();
-            const double xi = (fmax - f) / dAd;
-            const double beta = -dg / dAd;
+            double xi, beta, alpha_next;                              // (fmax - f)/dAd, -dg/dAd, dd/dAd (:954,:955,:966)
+            div3_same_divisor(fmax - f, -dg, dd, dAd, xi, beta, alpha_next);
             const double bhat = c.tau * beta + sqrt((c.tau * c.tau) * (beta * beta) + 2 * xi);
             const double hi = (c.sig2 < bhat) ? c.sig2 : bhat;        // Python min(bhat, sig2)
             if (hi != hi) { status = CCQP_ERR_RANGE; break; }
@@ -355,7 +366,7 @@ __device__ __forceinline__ void solve_one(const BatchedCtx& c, const double (&a)
             g += bk * ad;
             f += bk * bk * dg + 0.5 * (bk * bk) * dAd;                // :963 as written
             win.push(f, c.m);
-            alpha = dd / dAd;
+            alpha = alpha_next;
             iters++;
         }
         res = sqrt(dd_rep);
@@ -445,16 +456,43 @@ __global__ void __launch_bounds__(kBN, batched_min_ctas(SOLVER)) batched_kernel(
             asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(c.A + (size_t)prob * prob_elems),
                          "r"((unsigned)(prob_elems * 8)) : "memory");
     };
+#if CCQP_BATCHED_STAGE
+    const bool staged = c.tma_ok != 0;
+    unsigned phase = 0;
+    if (t == 0) { mbar_init(&sm.mbar, 1); mbar_fence_init(); }
+    auto issue_load = [&](int prob) {       // one 8n-byte bulk copy per row into the padded tile, one mbarrier
+        if (t == 0) mbar_expect_tx(&sm.mbar, (uint32_t)(prob_elems * 8));
+        if (t < n) bulk_g2s(sm.tile + t * kBPitch, c.A + (size_t)prob * prob_elems + (size_t)t * n, (uint32_t)(n * 8), &sm.mbar);
+    };
+#else
+    const bool staged = false;
+#endif
     if (t == 0) sm.next = (int)atomicAdd(c.counter, 1u);
     __syncthreads();
     int cur = sm.next;
+#if CCQP_BATCHED_STAGE
+    if (staged && cur < c.batch) { fence_proxy_async(); issue_load(cur); }
+#endif
     while (cur < c.batch) {
-        __syncthreads();                       // everyone has read sm.next
-        if (t == 0) sm.next = (int)atomicAdd(c.counter, 1u);
         // ---- register fill: this thread's sub-block; register row r <- row row0 + (r ^ cb) (see matvec)
         double a[kBRows][kBCols];
         const double* Ap = c.A + (size_t)cur * prob_elems;
-        if (c.vec_ok) {
+        if (staged) {
+#if CCQP_BATCHED_STAGE
+            mbar_wait(&sm.mbar, phase);
+            phase ^= 1u;
+            const uint32_t tb = smem_u32(sm.tile);
+#pragma unroll
+            for (int r = 0; r < kBRows; ++r) {
+                const int row = row0 + (r ^ cb);
+#pragma unroll
+                for (int j = 0; j < kBCols; j += 2) {
+                    if (row < n && col0 + j < n) lds_f64x2(tb + (uint32_t)(row * kBPitch + col0 + j) * 8u, a[r][j], a[r][j + 1]);
+                    else { a[r][j] = 0.0; a[r][j + 1] = 0.0; }
+                }
+            }
+#endif
+        } else if (c.vec_ok) {
 #pragma unroll
             for (int r = 0; r < kBRows; ++r) {
 #pragma unroll
@@ -474,6 +512,8 @@ __global__ void __launch_bounds__(kBN, batched_min_ctas(SOLVER)) batched_kernel(
                 for (int j = 0; j < kBCols; ++j)
                     a[r][j] = (row0 + (r ^ cb) < n && col0 + j < n) ? ldg_stream(Ap + (size_t)(row0 + (r ^ cb)) * n + col0 + j) : 0.0;
         }
+        __syncthreads();                       // everyone has read sm.next and, if staged, its part of the tile
+        if (t == 0) sm.next = (int)atomicAdd(c.counter, 1u);
         BState s;
         s.act = t < n;
         const size_t vo = (size_t)cur * n + t;
@@ -484,7 +524,12 @@ __global__ void __launch_bounds__(kBN, batched_min_ctas(SOLVER)) batched_kernel(
         s.cs = 1.0 / (3 * (double)n * kGd);
         __syncthreads();
         const int nxt = sm.next;
-        if (nxt < c.batch) prefetch_l2(nxt);   // lands in L2 while we iterate
+        if (nxt < c.batch) {                   // the next problem travels while this one iterates
+#if CCQP_BATCHED_STAGE
+            if (staged) { fence_proxy_async(); issue_load(nxt); } else
+#endif
+            prefetch_l2(nxt);
+        }
 
         double xsol = 0.0;
         BatchedOut o;
@@ -529,6 +574,7 @@ inline double sqrt_threshold(double tol, bool strict) {
 template <int SOLVER, bool WREG>
 inline cudaError_t launch_batched(const BatchedCtx& c, int sm_count, cudaStream_t stream) {
     int per_sm = 0;
+    cudaFuncSetAttribute(batched_kernel<SOLVER, WREG>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, batched_kernel<SOLVER, WREG>, kBN, 0);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
@@ -588,6 +634,7 @@ inline int batched_solve(cudaStream_t stream, int sm_count, void*, size_t, int s
     c.n_uniforms = (solver == CCQP_SOLVER_SPG) ? n_uniforms : 0;
     c.out = dout; c.counter = counter;
     c.batch = (int)batch; c.n = (int)n;
+    c.tma_ok = ((n * 8) % 16 == 0 && (reinterpret_cast<uintptr_t>(c.A) & 15) == 0) ? 1 : 0;
     c.vec_ok = (n % 4 == 0 && (reinterpret_cast<uintptr_t>(c.A) & 31) == 0) ? 1 : 0;
     c.pf_ok = ((n * n * 8) % 16 == 0 && (reinterpret_cast<uintptr_t>(c.A) & 15) == 0) ? 1 : 0;
     c.tol = prm.tol; c.max_mv = prm.max_mv; c.step = prm.step_size;

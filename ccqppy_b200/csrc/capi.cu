@@ -532,6 +532,25 @@ ccqp_status ccqp_solve_batched(ccqp_handle* h, int solver, const ccqp_params* pa
     return st;
 }
 
+namespace {
+__global__ void div3_kernel(const double* a0, const double* a1, const double* a2, const double* b, double* q0, double* q1,
+                            double* q2, long long count) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x)
+        div3_same_divisor(a0[i], a1[i], a2[i], b[i], q0[i], q1[i], q2[i]);
+}
+}  // namespace
+
+ccqp_status ccqp_debug_divide(ccqp_handle* h, const double* a0, const double* a1, const double* a2, const double* b,
+                            double* q0, double* q1, double* q2, int64_t count) {
+    if (!h || !a0 || !a1 || !a2 || !b || !q0 || !q1 || !q2 || count <= 0) return CCQP_ERR_INVALID_ARG;
+    CU(h, cudaSetDevice(h->device));
+    div3_kernel<<<h->sm_count * 4, 256, 0, h->stream>>>(a0, a1, a2, b, q0, q1, q2, count);
+    CU(h, cudaGetLastError());
+    CU(h, cudaStreamSynchronize(h->stream));
+    h->launches += 1;
+    return CCQP_OK;
+}
+
 struct CommDesc {                 // CCQP_COMM_DESC_BYTES = 128
     cudaIpcMemHandle_t handle;    // 64 bytes
     unsigned long long bytes;

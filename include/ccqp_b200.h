@@ -170,6 +170,11 @@ ccqp_status ccqp_project(ccqp_handle* h, const double* x, double* out, int memty
 /* out = normal_vector(x): solution_spaces.py:92,146,222,306,389,459,512. */
 ccqp_status ccqp_normal(ccqp_handle* h, const double* x, double* out, int memtype);
 
+/* q_k[i] = a_k[i] / b[i], k = 0..2, evaluated with the shared-reciprocal routine the batched SPG kernel uses
+ * for its three divisions by d.Ad (solvers.py:954,955,966); must equal IEEE division bit for bit. DEVICE pointers. */
+ccqp_status ccqp_debug_divide(ccqp_handle* h, const double* a0, const double* a1, const double* a2, const double* b,
+                            double* q0, double* q1, double* q2, int64_t count);
+
 /* ---- multi-GPU (row-sharded dense solves, one process per GPU) --------------------------------
  * Nothing in the reference corresponds to this (it is single-process NumPy).  A is row-sharded:
  * every rank calls ccqp_set_matrix() with its rows [row_begin, row_begin+n_rows) (boundaries on

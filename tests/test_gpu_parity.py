@@ -199,3 +199,38 @@ def test_dense_4096_config2_against_oracle(solver):
     assert abs(g["mv"] - o["mv"]) <= max(1, round(0.02 * o["mv"])), (g["mv"], o["mv"])
     if g["mv"] == o["mv"]:
         assert np.linalg.norm(g["solution"] - o["solution"]) <= 1e-9 * np.linalg.norm(o["solution"])
+
+
+def test_shared_divisor_division():
+    """The batched SPG kernel computes its three divisions by d.Ad with one shared reciprocal refinement
+    (common.cuh div3_same_divisor); the quotients must equal IEEE division bit for bit, including zero,
+    tiny, huge and non-finite operands."""
+    import ctypes
+    import torch
+    from ccqppy_b200 import _capi
+    g = torch.Generator(device="cuda").manual_seed(11)
+    n = 1 << 22
+    def rnd(scale_pow):
+        m = torch.randn(n, generator=g, device="cuda", dtype=torch.float64)
+        e = torch.randint(-scale_pow, scale_pow + 1, (n,), generator=g, device="cuda")
+        return torch.ldexp(m, e)
+    h = _capi.Handle()
+    special = torch.tensor([0.0, -0.0, 1.0, -1.0, 5e-324, -5e-324, 2.2250738585072014e-308, 1.7976931348623157e308,
+                            float("inf"), -float("inf"), float("nan"), 1e-300, 1e300, 3.0, 1.0 / 3.0], device="cuda",
+                           dtype=torch.float64)
+    for pw in (8, 300, 1060):
+        a = [rnd(pw) for _ in range(3)]
+        b = rnd(pw)
+        k = special.numel()
+        for j in range(3):
+            a[j][:k * k] = special.repeat_interleave(k) if j == 0 else special.repeat(k)
+        b[:k * k] = special.repeat(k)
+        b[k * k:2 * k * k] = special.repeat_interleave(k)
+        q = [torch.empty_like(b) for _ in range(3)]
+        P = lambda t: ctypes.c_void_p(t.data_ptr())
+        _capi.check(h.h, h.lib.ccqp_debug_divide(h.h, P(a[0]), P(a[1]), P(a[2]), P(b), P(q[0]), P(q[1]), P(q[2]), n))
+        for j in range(3):
+            ref = a[j] / b
+            same = (q[j].view(torch.int64) == ref.view(torch.int64)) | (torch.isnan(q[j]) & torch.isnan(ref))
+            assert bool(same.all()), (pw, j, int((~same).sum()))
+    h.close()
