@@ -417,21 +417,26 @@ ccqp_status ccqp_solve(ccqp_handle* h, int solver, const ccqp_params* params, co
     }
     float ms = 0.f;
     CU(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
-    if (dbg_timing && h->rank == 0) {      // mean phase durations of CTA 0 over iterations 8..39, microseconds
+    if (dbg_timing && h->rank == 0) {      // mean time between consecutive stamps of CTA 0 over the recorded iterations, us
         std::vector<long long> t(kDbgSlots * kDbgIters);
         CU(h, cudaMemcpy(t.data(), h->dbg.p, t.size() * 8, cudaMemcpyDeviceToHost));
-        double acc[5] = {0, 0, 0, 0, 0};
-        int cnt = 0;
-        for (int it = 8; it < 40; ++it) {
+        double acc[kDbgSlots] = {0};
+        int cnt = 0, used = 0;
+        for (int it = 1; it + 1 < kDbgIters; ++it) {
             const long long* r = &t[it * kDbgSlots];
             const long long* nx = &t[(it + 1) * kDbgSlots];
-            if (!r[0] || !r[4] || !nx[0]) continue;
-            for (int s = 0; s < 4; ++s) acc[s] += (r[s + 1] - r[s]) * 1e-3;
-            acc[4] += (nx[0] - r[4]) * 1e-3;
+            if (!r[0] || !nx[0]) continue;
+            int last = 0;
+            for (int s = 1; s < kDbgSlots; ++s) if (r[s]) { acc[last] += (r[s] - r[last]) * 1e-3; last = s; }
+            acc[last] += (nx[0] - r[last]) * 1e-3;
+            used = std::max(used, last + 1);
             ++cnt;
         }
-        if (cnt) fprintf(stderr, "[ccqp timing] world %d: pass %.1f  reduce2 %.1f  gemv %.1f  reduce1 %.1f  scalar %.1f  us (mean of %d iterations)\n",
-                         h->world, acc[0] / cnt, acc[1] / cnt, acc[2] / cnt, acc[3] / cnt, acc[4] / cnt, cnt);
+        if (cnt) {
+            fprintf(stderr, "[ccqp timing] world %d solver %d, us per phase (mean of %d iterations):", h->world, solver, cnt);
+            for (int s = 0; s < used; ++s) fprintf(stderr, " %.1f", acc[s] / cnt);
+            fprintf(stderr, "\n");
+        }
     }
     const DenseOut* o = reinterpret_cast<const DenseOut*>(h->out_host);
     std::memset(result, 0, sizeof(*result));

@@ -10,7 +10,7 @@
 //     round trip.
 //   * mat-vec phase (gemv_phase): the input vector is staged into shared memory in column panels
 //     by the TMA engine (cp.async.bulk + mbarrier, double buffered); A is streamed exactly once
-//     with 256-bit read-only loads (8 in flight per lane), FMA-accumulated per lane and reduced
+//     with 256-bit read-only loads (16 in flight per lane), FMA-accumulated per lane and reduced
 //     with warp shuffles; work inside a CTA is split into (row, column-segment) tasks so that all
 //     warps stay busy even when a CTA owns only a few rows (the 8-GPU row shard).  The epilogue
 //     functor of each solver fuses "+ b", the vector updates and the row-local dot products.
@@ -23,11 +23,16 @@
 
 namespace ccqp {
 
+// 256 threads x 16 loads in flight per lane (128 KB in flight per SM), not 512 x 4: the mat-vec loop is
+// inlined into solver programs that keep 50-70 registers of their own state live across it, and at
+// 128 registers per thread (512 threads) the loop of the larger programs spilled and streamed at
+// 4.3 TB/s (MPRGP) instead of 6.5; with 255 registers per thread every program runs the same loop.
+// In isolation 512 x 4 is 3 % faster (profiles/r01_gemv_sweep.log), inside the solvers it is not.
 #ifndef CCQP_DENSE_THREADS
-#define CCQP_DENSE_THREADS 512
+#define CCQP_DENSE_THREADS 256
 #endif
 #ifndef CCQP_UNROLL
-#define CCQP_UNROLL 4
+#define CCQP_UNROLL 16
 #endif
 constexpr int kDenseThreads = CCQP_DENSE_THREADS;
 constexpr int kDenseWarps = kDenseThreads / 32;
@@ -163,6 +168,26 @@ __device__ __forceinline__ unsigned long long and_sync(Kst& k, const DenseCtx& c
 // ------------------------------------------------------------------------------------------
 // mat-vec phase
 // ------------------------------------------------------------------------------------------
+// U consecutive 128-column chunks: all U 256-bit loads of the lane are issued before the first FMA
+template <bool kEF, int U>
+__device__ __forceinline__ void dot_chunks(const double* ap, const double* vp, double& a0, double& a1, double& a2,
+                                           double& a3) {
+    double r[U][4];
+#pragma unroll
+    for (int u = 0; u < U; ++u) ldg256_stream<kEF>(ap + (size_t)u * 128, r[u]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const double4 v = *reinterpret_cast<const double4*>(vp + (size_t)u * 128);
+        a0 = fma(r[u][0], v.x, a0);
+        a1 = fma(r[u][1], v.y, a1);
+        a2 = fma(r[u][2], v.z, a2);
+        a3 = fma(r[u][3], v.w, a3);
+    }
+}
+
+// One (row, segment) task of a warp: lanes own 4 consecutive columns of every 128-column chunk.
+// Chunks are consumed in order (kUnroll at a time, then 8/4/2/1 for the remainder), so the
+// summation order does not depend on the blocking.
 template <bool kEF>
 __device__ __forceinline__ double dot_seg_aligned(const double* __restrict__ arow, const double* vs, int ncol,
                                                   int lane) {
@@ -171,28 +196,11 @@ __device__ __forceinline__ double dot_seg_aligned(const double* __restrict__ aro
     const double* ap = arow + lane * 4;
     const double* vp = vs + lane * 4;
     int c = 0;
-    for (; c + kUnroll <= nchunk; c += kUnroll) {
-        double r[kUnroll][4];
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u) ldg256_stream<kEF>(ap + (size_t)(c + u) * 128, r[u]);
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u) {
-            const double4 v = *reinterpret_cast<const double4*>(vp + (size_t)(c + u) * 128);
-            a0 = fma(r[u][0], v.x, a0);
-            a1 = fma(r[u][1], v.y, a1);
-            a2 = fma(r[u][2], v.z, a2);
-            a3 = fma(r[u][3], v.w, a3);
-        }
-    }
-    for (; c < nchunk; ++c) {
-        double r[4];
-        ldg256_stream<kEF>(ap + (size_t)c * 128, r);
-        const double4 v = *reinterpret_cast<const double4*>(vp + (size_t)c * 128);
-        a0 = fma(r[0], v.x, a0);
-        a1 = fma(r[1], v.y, a1);
-        a2 = fma(r[2], v.z, a2);
-        a3 = fma(r[3], v.w, a3);
-    }
+    for (; c + kUnroll <= nchunk; c += kUnroll) dot_chunks<kEF, kUnroll>(ap + (size_t)c * 128, vp + (size_t)c * 128, a0, a1, a2, a3);
+    if (kUnroll > 8 && c + 8 <= nchunk) { dot_chunks<kEF, 8>(ap + (size_t)c * 128, vp + (size_t)c * 128, a0, a1, a2, a3); c += 8; }
+    if (kUnroll > 4 && c + 4 <= nchunk) { dot_chunks<kEF, 4>(ap + (size_t)c * 128, vp + (size_t)c * 128, a0, a1, a2, a3); c += 4; }
+    if (kUnroll > 2 && c + 2 <= nchunk) { dot_chunks<kEF, 2>(ap + (size_t)c * 128, vp + (size_t)c * 128, a0, a1, a2, a3); c += 2; }
+    if (c < nchunk) { dot_chunks<kEF, 1>(ap + (size_t)c * 128, vp + (size_t)c * 128, a0, a1, a2, a3); c += 1; }
     const int col = (nchunk << 7) + lane * 4;
     if (col < ncol) {
         a0 = fma(ldg_stream(arow + col), vs[col], a0);
@@ -677,8 +685,10 @@ __device__ void solve_mprgp(Kst& k, const DenseCtx& c) {
                      [&](int i, double t, double pr) { p[i] = is_close(t, pr) ? ld_cg(gk + i) : 0.0; });
         barrier_only<false>(k, c);
         for (;;) {
+            dbg_stamp(c, k.iters, 0);
             gemv_into(k, c, xk, gk, [&](int r, double s) { return s + b[r]; });
             k.mv += 1;
+            dbg_stamp(c, k.iters, 1);
             if (hit_max(k, c)) break;
             // delta = isclose(xk, P(xk)); psi = delta*gk   (:1093-1094)
             double q3[3] = {0.0, 0.0, 0.0};          // psi.psi, psi.p, #(!delta)
@@ -692,6 +702,7 @@ __device__ void solve_mprgp(Kst& k, const DenseCtx& c) {
                              dl[i] = cl ? 1.0 : 0.0;
                          });
             reduce_sync<3, false>(k, c, q3);
+            dbg_stamp(c, k.iters, 2);
             if (c.T.has_cone_ref) { status = 6; break; }   // normal_vector raises (:1095, ss:465)
             double betbet = 0.0;
             if (q3[2] > 0.0) {
@@ -723,6 +734,7 @@ __device__ void solve_mprgp(Kst& k, const DenseCtx& c) {
                         barrier_only<false>(k, c);
                     }
                 }
+                dbg_stamp(c, k.iters, 3);
                 if (hit_max(k, c)) break;
                 const double pAp = s1[0];
                 const double acg = q3[1] / pAp;
@@ -733,6 +745,7 @@ __device__ void solve_mprgp(Kst& k, const DenseCtx& c) {
                     for (int q = 0; q < 64; ++q) af *= 0.5;
                     if (pass >= 20) break;            // af == 0 by now; the reference would spin forever
                 }
+                dbg_stamp(c, k.iters, 4);
                 if (acg <= af) {
                     // conjugate-gradient step :1121-1135
                     project_pass(c.T, k.gtid, k.gstride, k.sm.scratch,
@@ -768,8 +781,10 @@ __device__ void solve_mprgp(Kst& k, const DenseCtx& c) {
                                  },
                                  [&](int i, double, double pr) { xn[i] = pr; });
                     barrier_only<false>(k, c);
+                    dbg_stamp(c, k.iters, 5);
                     gemv_into(k, c, xn, gn, [&](int r, double s) { return s + b[r]; });
                     k.mv += 1;
+                    dbg_stamp(c, k.iters, 6);
                     if (hit_max(k, c)) break;
                     project_pass(c.T, k.gtid, k.gstride, k.sm.scratch, [&](int i) { return ld_cg(xn + i); },
                                  [&](int i, double t, double pr) { p[i] = is_close(t, pr) ? ld_cg(gn + i) : 0.0; });

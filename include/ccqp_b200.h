@@ -177,16 +177,17 @@ ccqp_status ccqp_debug_divide(ccqp_handle* h, const double* a0, const double* a1
 
 /* ---- multi-GPU (row-sharded dense solves, one process per GPU) --------------------------------
  * Nothing in the reference corresponds to this (it is single-process NumPy).  A is row-sharded:
- * every rank calls ccqp_set_matrix() with its rows [row_begin, row_begin+n_rows) (boundaries on
- * projection-block boundaries) and the FULL projection table.  Setup, once per problem size:
+ * every rank calls ccqp_set_matrix() with its rows [row_begin, row_begin+n_rows) and the FULL
+ * projection table; the vectors are kept in full on every rank.  Setup, once per problem size:
  *   1. ccqp_comm_export(): allocate this rank's exchange buffer, get an opaque descriptor (CUDA IPC)
  *   2. the host all-gathers the descriptors (torch.distributed / MPI / files: the ABI does not care)
  *   3. ccqp_comm_attach(): map every peer's buffer over NVLink
  * Per solve: ccqp_comm_prepare() (clears the buffer), a HOST barrier across ranks, then ccqp_solve()
- * on every rank with the same arguments.  Inside the solver kernel each rank writes its slice of
- * every mat-vec input vector and its scalar partial sums straight into the peers' buffers and the
- * ranks synchronise through flags in peer memory: no collective launches inside the loop.  Every
- * rank returns the full solution and identical result fields. */
+ * on every rank with the same arguments.  Inside the solver kernel each rank writes the rows of
+ * every mat-vec result it computes straight into the peers' buffers (the all-gather, fused into the
+ * mat-vec epilogue) and the sync that closes the mat-vec phase exchanges the scalar partial sums and
+ * synchronises the ranks through 8-byte {data, epoch} packets in peer memory: no collective
+ * launches inside the loop.  Every rank returns the full solution and identical result fields. */
 #define CCQP_COMM_DESC_BYTES 128
 ccqp_status ccqp_comm_export(ccqp_handle* h, int rank, int world, int64_t n, void* desc);
 ccqp_status ccqp_comm_attach(ccqp_handle* h, const void* all_descs /* world * CCQP_COMM_DESC_BYTES */);
