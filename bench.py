@@ -170,23 +170,26 @@ def run_reference_arm(args, rank):
 
 
 # ---------------------------------------------------------------------------------------------
-def bench_batched(device, steps, warmup):
+def bench_batched(device, steps, warmup, batch=None, seed=1, reduce_max=None):
+    """Config 4.  `batch` problems on this GPU; with `reduce_max` (multi-GPU) the slowest rank's time counts and
+    the rates are for the whole job of BATCH problems."""
     import torch
     from ccqppy_b200 import solvers
-    g = torch.Generator(device=device).manual_seed(1)
+    local = BATCH if batch is None else batch
+    g = torch.Generator(device=device).manual_seed(seed)
     out = {}
     chunk = 8192
-    A = torch.empty((BATCH, NB, NB), device=device, dtype=torch.float64)
-    b = torch.empty((BATCH, NB), device=device, dtype=torch.float64)
-    for s in range(0, BATCH, chunk):
-        e = min(BATCH, s + chunk)
+    A = torch.empty((local, NB, NB), device=device, dtype=torch.float64)
+    b = torch.empty((local, NB), device=device, dtype=torch.float64)
+    for s in range(0, local, chunk):
+        e = min(local, s + chunk)
         G = torch.randn((e - s, NB, NB), generator=g, device=device, dtype=torch.float64)
         A[s:e] = G @ G.transpose(1, 2) / NB + torch.eye(NB, device=device, dtype=torch.float64)
         xs = 1 - 4 * torch.rand((e - s, NB), generator=g, device=device, dtype=torch.float64)
         b[s:e] = -(A[s:e] @ xs.unsqueeze(-1)).squeeze(-1)
     lb, ub = -torch.ones_like(b), torch.ones_like(b)
     K = 256
-    uni = torch.rand((BATCH, K), generator=g, device=device, dtype=torch.float64)
+    uni = torch.rand((local, K), generator=g, device=device, dtype=torch.float64)
     peak, _ = measured_peak()
     for name, cls in (("BBPGD", solvers.CCQPSolverBBPGD), ("SPG", solvers.CCQPSolverSPG)):
         s = cls(1e-8, 5000)
@@ -199,7 +202,10 @@ def bench_batched(device, steps, warmup):
         t = float(np.mean(times))
         hbm = s.solution_hbm_bytes
         flops = 2.0 * NB * NB * s.solution_gemv_count
-        out[name] = dict(qps=BATCH / t, ms=1e3 * t, mean_mv=float(np.mean(s.solution_num_matrix_vector_multiplications)),
+        total = local
+        if reduce_max is not None:      # slowest rank's time; bytes, flops and problems of all ranks
+            t, hbm, flops, total = reduce_max(t, hbm, flops, local)
+        out[name] = dict(qps=total / t, ms=1e3 * t, mean_mv=float(np.mean(s.solution_num_matrix_vector_multiplications)),
                          converged=bool(np.all(s.solution_converged)), hbm_GBps=hbm / t / 1e9, hbm_frac=hbm / t / 1e9 / peak,
                          fp64_TFLOPs=flops / t / 1e12)
     return out
@@ -230,6 +236,8 @@ def main():
     device = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=device)
     n = N_DENSE
     t_gen = time.time()
@@ -391,6 +399,27 @@ def main():
         tt = torch.tensor([time.perf_counter() - t0], device=device, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e_dt = float(tt[0])
+        if not args.no_batched:
+            del runner, A_host
+            torch.cuda.empty_cache()
+            from ccqppy_b200.dist import batch_range
+
+            def reduce_max(t, hbm, flops, cnt):
+                tt = torch.tensor([t], device=device, dtype=torch.float64)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                ss = torch.tensor([hbm, flops, cnt], device=device, dtype=torch.float64)
+                dist.all_reduce(ss, op=dist.ReduceOp.SUM)
+                return float(tt[0]), float(ss[0]), float(ss[1]), float(ss[2])
+            i0, i1 = batch_range(BATCH, rank, world)
+            try:
+                line["batched"] = bench_batched(device, steps=3, warmup=2, batch=i1 - i0, seed=1 + rank, reduce_max=reduce_max)
+                line["batched"]["workload"] = ("%d box-QPs n=%d split contiguously over %d GPUs (no communication), rates for the "
+                                               "whole job, hbm_frac per job against %d x the per-GPU peak" % (BATCH, NB, world, world))
+                for v in line["batched"].values():
+                    if isinstance(v, dict):
+                        v["hbm_frac"] = v["hbm_frac"] / world
+            except Exception as ex:
+                line["batched"] = dict(error=repr(ex))
         line["e2e"] = dict(value=e_mvs / e_dt, unit="iterations/s",
                            h2d_bytes_per_step=8 * n * n + world * (8 * n + 8 * MAX_MV), d2h_bytes_per_step=world * (8 * n + 72),
                            steps=e2e_steps, s_per_solve=e_dt / e2e_steps,

@@ -632,13 +632,46 @@ __device__ unsigned long long bisect_mask(Kst& k, const DenseCtx& c, const doubl
             if (!is_close(yf, clamp_elem(kd, yf, lo, hi))) m &= ~(1ull << j);
         }
     }
-    if (!T.all_elementwise) {
+    // small norm blocks (Sphere / Cone / SOC with <= 8 entries, the friction-style case): one thread per
+    // block keeps x and p of the block in registers and tests all 64 step lengths itself
+    for (int sidx = k.gtid; sidx < T.nsmall; sidx += k.gstride) {
+        const int bl = T.small_ids[sidx];
+        const int off = T.boff[bl], dim = T.bdim[bl];
+        double xb[kSmallDim], pb[kSmallDim];
+#pragma unroll
+        for (int j = 0; j < kSmallDim; ++j) if (j < dim) { xb[j] = ld_cg(x + off + j); pb[j] = ld_cg(p + off + j); }
+        NormRule R;
+        R.kind = T.bkind[bl]; R.par = T.bpar[bl];
+        const int nsq = (R.kind == kSoc) ? dim - 1 : dim;
+        double a = af;
+        for (int step = 0; step < 64; ++step, a *= 0.5) {
+            double t[kSmallDim];
+            double ss = 0.0;
+#pragma unroll
+            for (int j = 0; j < kSmallDim; ++j) {
+                if (j < dim) {
+                    t[j] = xb[j] - a * pb[j];
+                    if (j < nsq) ss = (j == 0) ? t[j] * t[j] : fma(t[j], t[j], ss);     // same chain as project_pass
+                }
+            }
+            R.r = sqrt(ss);
+            R.last = 0.0;
+#pragma unroll
+            for (int j = 0; j < kSmallDim; ++j) if (j == dim - 1) R.last = t[j];
+            R.finish();
+            bool ok = true;
+#pragma unroll
+            for (int j = 0; j < kSmallDim; ++j) if (j < dim && !is_close(t[j], R.apply(t[j], j == dim - 1))) ok = false;
+            if (!ok) m &= ~(1ull << step);
+        }
+    }
+    if (T.nbig > 0) {   // one CTA per large norm block: one projection pass per step length (rare)
         double a = af;
         for (int j = 0; j < 64; ++j, a *= 0.5) {
             bool ok = true;
-            project_pass<false>(T, k.gtid, k.gstride, k.sm.scratch,
-                                [&](int i) { return ld_cg(x + i) - a * ld_cg(p + i); },
-                                [&](int, double t, double pr) { if (!is_close(t, pr)) ok = false; });
+            project_pass<false, false>(T, k.gtid, k.gstride, k.sm.scratch,
+                                       [&](int i) { return ld_cg(x + i) - a * ld_cg(p + i); },
+                                       [&](int, double t, double pr) { if (!is_close(t, pr)) ok = false; });
             if (!ok) m &= ~(1ull << j);
         }
     }

@@ -91,7 +91,9 @@ struct NormRule {
 //   gtid/gstride : global thread id / total thread count of the grid
 //   scratch      : 64 doubles of shared memory (only touched when big norm blocks exist)
 // Every thread of every CTA must call it (it contains __syncthreads() when nbig > 0).
-template <bool kDoElem = true, class Arg, class Sink>
+// kDoElem / kDoSmall = false skip the elementwise kinds / the small norm blocks (MPRGP's bisection
+// handles those itself).
+template <bool kDoElem = true, bool kDoSmall = true, class Arg, class Sink>
 __device__ __forceinline__ void project_pass(const ProjTable& T, int gtid, int gstride, double* scratch,
                                              Arg arg, Sink sink) {
     if (kDoElem) for (int i = T.e0 + gtid; i < T.e1; i += gstride) {
@@ -101,7 +103,7 @@ __device__ __forceinline__ void project_pass(const ProjTable& T, int gtid, int g
         sink(i, t, clamp_elem(k, t, T.lo[i], T.hi[i]));
     }
     if (T.all_elementwise) return;
-    for (int s = gtid; s < T.nsmall; s += gstride) {
+    if (kDoSmall) for (int s = gtid; s < T.nsmall; s += gstride) {
         const int b = T.small_ids[s];
         const int off = T.boff[b], dim = T.bdim[b];
         if (off < T.e0 || off >= T.e1) continue;

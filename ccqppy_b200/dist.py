@@ -52,6 +52,51 @@ def exchange_descriptors(desc, group=None):
     return b"".join(out)
 
 
+def batch_range(batch, rank, world):
+    """Contiguous share [i0, i1) of `batch` independent problems for `rank` (sizes differ by at most 1)."""
+    base, extra = divmod(int(batch), int(world))
+    i0 = rank * base + min(rank, extra)
+    return i0, i0 + base + (1 if rank < extra else 0)
+
+
+def solve_batched_sharded(solver, A, b, lower_bound, upper_bound, x0=None, seeds=None, uniforms=None, n_uniforms=256,
+                          gather=True, group=None):
+    """Batched mode on several GPUs: the problems are independent, so every rank solves its contiguous
+    share on its own GPU and there is NO communication on the data path.
+    The arguments are the FULL batch (NumPy / torch; each rank only touches its share).  With
+    `gather` the per-problem results are all-gathered afterwards so that every rank returns the whole
+    batch; otherwise each rank keeps its share.  Returns (solution, residual, converged, mv, (i0, i1))."""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    batch = int(A.shape[0])
+    i0, i1 = batch_range(batch, rank, world)
+    cut = lambda v: None if v is None else v[i0:i1]
+    if seeds is None and uniforms is None:
+        seeds = np.arange(batch)
+    solver.solve_batched(cut(A), cut(b), cut(lower_bound), cut(upper_bound), x0=cut(x0), seeds=cut(seeds),
+                         uniforms=cut(uniforms), n_uniforms=n_uniforms)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    x = solver.solution if hasattr(solver.solution, "is_cuda") else torch.from_numpy(np.ascontiguousarray(solver.solution))
+    x = x.to(dev)
+    res = torch.from_numpy(np.ascontiguousarray(solver.solution_residual)).to(dev)
+    conv = torch.from_numpy(solver.solution_converged.astype(np.int64)).to(dev)
+    mv = torch.from_numpy(np.ascontiguousarray(solver.solution_num_matrix_vector_multiplications, dtype=np.int64)).to(dev)
+    if not gather or world == 1:
+        return x, res, conv.bool(), mv, (i0, i1)
+    n = int(x.shape[1])
+    cap = (batch + world - 1) // world                      # all_gather wants equal shapes: pad the short shares
+    pack = torch.zeros((cap, n + 3), dtype=torch.float64, device=dev)
+    pack[:i1 - i0, :n] = x
+    pack[:i1 - i0, n] = res
+    pack[:i1 - i0, n + 1] = conv.double()
+    pack[:i1 - i0, n + 2] = mv.double()
+    parts = [torch.empty_like(pack) for _ in range(world)]
+    dist.all_gather(parts, pack, group=group)
+    full = torch.cat([parts[r][:batch_range(batch, r, world)[1] - batch_range(batch, r, world)[0]] for r in range(world)])
+    return full[:, :n].contiguous(), full[:, n].contiguous(), full[:, n + 1] > 0.5, full[:, n + 2].long(), (i0, i1)
+
+
 class ShardedResult:
     """Result fields of one sharded solve (same names as the solver properties)."""
 

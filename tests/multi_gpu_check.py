@@ -18,7 +18,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import problems as pr                                   # noqa: E402
 from helpers import op_from_table, make_solver          # noqa: E402
-from ccqppy_b200.dist import ShardedSolver              # noqa: E402
+from ccqppy_b200.dist import ShardedSolver, solve_batched_sharded, batch_range   # noqa: E402
 from oracle import ccqp_oracle as orc                   # noqa: E402
 
 
@@ -70,6 +70,42 @@ def main():
                                ranks_identical=ident, ok=good, gpu_ms=1e3 * r.solution_gpu_time,
                                single_ms=1e3 * one.solution_gpu_time))
             runner.close()
+    # ---- re-upload of a row shard from (pinned) host memory: same answers as the resident shard
+    n = 2048
+    A, b = pr.shift_problem(n, 6)
+    tab = pr.box_table(n)
+    op = op_from_table(tab)
+    runner = ShardedSolver(make_solver(pr.BBPGD, 1e-7, 500), torch.from_numpy(A).to(dev), op, rank, world, dev)
+    r_dev = runner.solve(b)
+    r0, r1 = runner.ranges[rank]
+    runner.set_matrix(torch.from_numpy(A[r0:r1].copy()).pin_memory())
+    r_host = runner.solve(b)
+    runner.set_matrix(np.ascontiguousarray(2.0 * A[r0:r1]))           # a different Hessian must give a different answer
+    r_other = runner.solve(b)
+    good = bool(torch.equal(r_dev.solution, r_host.solution)) and not bool(torch.equal(r_dev.solution, r_other.solution))
+    o = orc.solve(pr.BBPGD, 2.0 * A, b, blocks=tab.blocks, params=tab.params, tol=1e-7, max_mv=500)
+    good = good and float(np.linalg.norm(r_other.solution.cpu().numpy() - o["solution"]) / np.linalg.norm(o["solution"])) < 1e-9
+    ok = ok and good
+    report.append(dict(table="box", solver="set_matrix", mv=r_host.solution_num_matrix_vector_multiplications,
+                       mv_single=r_dev.solution_num_matrix_vector_multiplications, err=0.0, ok=good, gpu_ms=0.0, single_ms=0.0))
+    runner.close()
+
+    # ---- batched mode split over the ranks (no communication on the data path) against one GPU
+    batch, nb = 37, 64
+    Ab = np.empty((batch, nb, nb)); bb = np.empty((batch, nb))
+    for i in range(batch):
+        Ab[i], bb[i] = pr.shift_problem(nb, 50 + i)
+    lb, ub = -np.ones((batch, nb)), np.ones((batch, nb))
+    for solver in (pr.BBPGD, pr.SPG):
+        one = make_solver(solver, 1e-8, 5000)
+        one.solve_batched(Ab, bb, lb, ub, seeds=np.arange(batch))
+        x, res, conv, mv, (i0, i1) = solve_batched_sharded(make_solver(solver, 1e-8, 5000), Ab, bb, lb, ub, seeds=np.arange(batch))
+        good = (i0, i1) == batch_range(batch, rank, world) and np.array_equal(x.cpu().numpy(), np.asarray(one.solution)) \
+            and np.array_equal(mv.cpu().numpy(), one.solution_num_matrix_vector_multiplications) and bool(conv.all())
+        ok = ok and good
+        report.append(dict(table="batched", solver=pr.SOLVER_NAMES[solver], mv=int(mv.sum()), mv_single=int(one.solution_num_matrix_vector_multiplications.sum()),
+                           err=0.0, ok=good, gpu_ms=0.0, single_ms=0.0))
+
     flags = [None] * world
     dist.all_gather_object(flags, ok)
     if rank == 0:

@@ -8,7 +8,7 @@ import pytest
 import torch.multiprocessing as mp
 
 import problems as pr
-from ccqppy_b200.dist import shard_rows
+from ccqppy_b200.dist import shard_rows, batch_range
 
 
 def test_split_elementwise_is_even():
@@ -40,6 +40,15 @@ def test_split_mixed_and_impossible():
                 assert not (off < r0 < off + dim) and not (off < r1 < off + dim)
     with pytest.raises(ValueError):
         shard_rows(pr.sphere_table(100).rows, 100, 2)     # one whole-vector sphere cannot be split
+
+
+def test_batch_split_is_contiguous_and_even():
+    for batch, world in ((65536, 8), (10, 4), (7, 8), (1, 2), (100, 3)):
+        r = [batch_range(batch, k, world) for k in range(world)]
+        assert r[0][0] == 0 and r[-1][1] == batch
+        assert all(a[1] == b[0] for a, b in zip(r[:-1], r[1:]))
+        sizes = [b - a for a, b in r]
+        assert max(sizes) - min(sizes) <= 1
 
 
 def _worker(rank, world, port, q):

@@ -234,3 +234,35 @@ def test_shared_divisor_division():
             same = (q[j].view(torch.int64) == ref.view(torch.int64)) | (torch.isnan(q[j]) & torch.isnan(ref))
             assert bool(same.all()), (pw, j, int((~same).sum()))
     h.close()
+
+
+def test_benchmark_driver_matches_oracle_on_the_reference_study():
+    """The counterpart of benchmarks/benchmark_random_ccqp.py (row f-2): a small slice of the reference's
+    disjoint-constraint study; every (solver, constraint type, size, trial) cell must reproduce the oracle's
+    mat-vec count and converged flag on the same Wishart problem."""
+    from ccqppy_b200 import benchmark, solution_spaces as ss
+    study = benchmark.benchmark_disjoint_constraints(problem_sizes=[3, 6, 12], num_random_trials=3)
+    summ = study.summary()
+    assert summ["sizes"] == [3, 6, 12] and len(summ["solvers"]) == 7 and len(summ["proj_types"]) == 5
+    kinds = [pr.IDENTITY, pr.LOWER, pr.UPPER, pr.SPHERE, pr.BOX]
+    ids = [pr.PGD, pr.APGD, pr.APGD_AR, pr.BBPGD, pr.BBPGDF, pr.MPRGP]      # SPG consumes the global RNG: checked elsewhere
+    pos = [0, 1, 2, 3, 4, 6]
+    cells = same_mv = same_flag = 0
+    for pi, n in enumerate([3, 6, 12]):
+        for trial in range(3):
+            A, b = study.generate_random_convex_quadratic_func(n, trial)
+            for ti, kind in enumerate(kinds):
+                tab = pr.Table()
+                for _ in range(n // 3):
+                    if kind == pr.IDENTITY: tab.add(kind, 3)
+                    elif kind == pr.LOWER: tab.add(kind, 3, -1.0)
+                    elif kind in (pr.UPPER, pr.SPHERE): tab.add(kind, 3, 1.0)
+                    else: tab.add(kind, 3, -1.0, 1.0)
+                for sp, sid in zip(pos, ids):
+                    o = orc.solve(sid, A, b, blocks=tab.blocks, params=tab.params, tol=1e-5, max_mv=5000)
+                    cells += 1
+                    same_flag += bool(study.problem_converged[sp, ti, pi, trial]) == o["converged"]
+                    same_mv += study.problem_num_matrix_vector_mults[sp, ti, pi, trial] == o["mv"]
+    # Wishart(df = n) at n <= 12 can be nearly singular (the reference's own study): BB / restart decisions
+    # then flip on rounding-level differences, so a minority of cells takes a different number of steps
+    assert cells == 270 and same_flag >= 0.97 * cells and same_mv >= 0.85 * cells, (cells, same_flag, same_mv)
