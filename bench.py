@@ -211,6 +211,26 @@ def bench_batched(device, steps, warmup, batch=None, seed=1, reduce_max=None):
     return out
 
 
+def batched_cpu_baseline(sample=192):
+    """The reference's way of doing config 4: a Python loop of solve() calls, one problem at a time (the port in
+    oracle/, one core -- the reference has no batching or threading), on a bounded sample of the same generator."""
+    from oracle import ccqp_oracle as orc
+    import problems as pr
+    tab = pr.box_table(NB)
+    probs = [pr.shift_problem(NB, 1000 + i) for i in range(sample)]
+    out = {}
+    for name, sid in (("BBPGD", orc.BBPGD), ("SPG", orc.SPG)):
+        t0 = time.perf_counter()
+        mv = 0
+        for i, (A, b) in enumerate(probs):
+            mv += orc.solve(sid, A, b, blocks=tab.blocks, params=tab.params, tol=1e-8, max_mv=5000,
+                            uniforms=pr.spg_uniforms(i, 512))["mv"]
+        dt = time.perf_counter() - t0
+        out[name] = dict(qps=sample / dt, mean_mv=mv / sample)
+    out.update(cores=1, kind="port", sample="%d problems of n=%d solved one after the other, as the reference would" % (sample, NB))
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -370,6 +390,8 @@ def main():
             try:
                 line["batched"] = bench_batched(device, steps=3, warmup=2)
                 line["batched"]["workload"] = "%d box-QPs n=%d, A=GG^T/n+I, tol 1e-8, persistent per-CTA kernel" % (BATCH, NB)
+                if not args.no_cpu_baseline:
+                    line["batched"]["cpu_baseline"] = batched_cpu_baseline()
             except Exception as ex:   # never lose the headline line
                 line["batched"] = dict(error=repr(ex))
     else:

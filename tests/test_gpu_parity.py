@@ -228,6 +228,7 @@ def test_shared_divisor_division():
         b[k * k:2 * k * k] = special.repeat_interleave(k)
         q = [torch.empty_like(b) for _ in range(3)]
         P = lambda t: ctypes.c_void_p(t.data_ptr())
+        torch.cuda.synchronize()      # a raw handle runs on its own stream, not on torch's
         _capi.check(h.h, h.lib.ccqp_debug_divide(h.h, P(a[0]), P(a[1]), P(a[2]), P(b), P(q[0]), P(q[1]), P(q[2]), n))
         for j in range(3):
             ref = a[j] / b
@@ -266,3 +267,32 @@ def test_benchmark_driver_matches_oracle_on_the_reference_study():
     # Wishart(df = n) at n <= 12 can be nearly singular (the reference's own study): BB / restart decisions
     # then flip on rounding-level differences, so a minority of cells takes a different number of steps
     assert cells == 270 and same_flag >= 0.97 * cells and same_mv >= 0.85 * cells, (cells, same_flag, same_mv)
+
+
+@pytest.mark.parametrize("n", [5, 63, 1023, 2051])
+def test_device_matrix_with_unaligned_rows(n):
+    """A CUDA tensor whose rows are not 32-byte aligned (odd n) is borrowed in place and goes through the
+    64-bit-load path of the mat-vec; results must equal the host-upload path (which pads the rows)."""
+    import torch
+    A, b = pr.shift_problem(n, 21)
+    tab = pr.box_table(n)
+    for solver in (pr.BBPGD, pr.SPG, pr.MPRGP):
+        host = run_gpu(solver, A, b, tab, tol=1e-7, max_mv=800, spg_seed=4)
+        s = make_solver(solver, 1e-7, 800)
+        np.random.seed(4)
+        s.solve(torch.from_numpy(A).cuda(), torch.from_numpy(b).cuda(), convex_proj_op=op_from_table(tab))
+        assert s.solution_num_matrix_vector_multiplications == host["mv"]
+        np.testing.assert_allclose(s.solution.cpu().numpy(), host["solution"], rtol=1e-12, atol=1e-14)
+    # leading dimension larger than n (a window of a bigger device matrix), straight through the C-ABI
+    import ctypes
+    from ccqppy_b200 import _capi
+    big = torch.zeros((n, n + 3), device="cuda", dtype=torch.float64)
+    big[:, :n] = torch.from_numpy(A).cuda()
+    v = np.random.default_rng(1).standard_normal(n)
+    torch.cuda.synchronize()          # a raw handle runs on its own stream, not on torch's
+    h = _capi.Handle()
+    _capi.check(h.h, h.lib.ccqp_set_matrix(h.h, ctypes.c_void_p(big.data_ptr()), n, n + 3, 0, n, _capi.MEM_DEVICE))
+    y = np.empty(n)
+    _capi.check(h.h, h.lib.ccqp_gemv(h.h, ctypes.c_void_p(v.ctypes.data), ctypes.c_void_p(y.ctypes.data), _capi.MEM_HOST))
+    h.close()
+    np.testing.assert_allclose(y, A @ v, rtol=1e-12, atol=1e-12)

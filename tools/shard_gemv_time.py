@@ -17,6 +17,7 @@ v[:n] = torch.randn(n, generator=g, device=dev, dtype=torch.float64)
 y = torch.zeros(n + 64, device=dev, dtype=torch.float64)
 for P in (1, 2, 4, 8):
     rows = n // P
+    torch.cuda.synchronize()          # a raw handle runs on its own stream, not on torch's
     h = _capi.Handle()
     _capi.check(h.h, h.lib.ccqp_set_matrix(h.h, C.c_void_p(A.data_ptr()), n, n, 0, rows, 1))
     sec = C.c_double()
