@@ -42,6 +42,13 @@ struct ccqp_handle {
     // matrix shard
     const double* dA = nullptr;
     DevBuf a_own;
+    // operator-form (CSR) alternative to dA
+    const long long* d_ptr = nullptr;
+    const int* d_idx = nullptr;
+    const double* d_val = nullptr;
+    DevBuf ptr_own, idx_own, val_own;
+    long long nnz = 0;
+    bool have_matrix() const { return dA != nullptr || d_val != nullptr; }
     long long n = 0, lda = 0, row0 = 0, nrows = 0;
     // projection
     bool have_proj = false;
@@ -117,6 +124,11 @@ Tiling choose_tiling(const ccqp_handle* h) {
     Tiling t;
     const long long n = h->n, nrows = h->nrows;
     t.grid = (int)std::max(1LL, std::min<long long>(h->sm_count, nrows));
+    if (h->d_val) {     // CSR: no panels of the input vector in shared memory
+        t.CW = 128; t.SW = 128; t.np = 1; t.nseg = 1; t.rows_max = 1;
+        t.smem = dense_smem_bytes(t.CW, t.rows_max, t.nseg);
+        return t;
+    }
     t.rows_max = (int)((nrows + t.grid - 1) / t.grid) + 1;
     t.CW = (int)std::min<long long>(8192, round_up(n, 128));
     t.SW = std::min(2048, t.CW);
@@ -140,6 +152,14 @@ void fill_ctx(ccqp_handle* h, DenseCtx& c, const Tiling& t) {
     double* w = reinterpret_cast<double*>(h->work.as<char>() + kSymVecOff);
     c.A = h->dA; c.lda = h->lda; c.n = (int)h->n; c.row0 = (int)h->row0; c.nrows = (int)h->nrows;
     c.aligned = ((reinterpret_cast<uintptr_t>(h->dA) & 31) == 0 && (h->lda % 4) == 0) ? 1 : 0;
+    c.csr_ptr = h->d_ptr; c.csr_idx = h->d_idx; c.csr_val = h->d_val;
+    {
+        const double mean = h->d_val ? (double)h->nnz / (double)std::max<long long>(h->nrows, 1) : 0.0;
+        // few lanes per row: with 8 warps per SM the loop lives on instruction-level parallelism (16 entries in
+        // flight per lane), so a lane should own tens of entries (sweep: tools/bench_sparse.py with CCQP_CSR_GROUP)
+        c.csr_group = mean >= 1024 ? 32 : mean >= 512 ? 16 : mean >= 256 ? 8 : mean >= 128 ? 4 : 2;
+        if (const char* e = getenv("CCQP_CSR_GROUP")) c.csr_group = atoi(e);
+    }
     c.b = w + W_B * h->npad; c.x0 = w + W_X0 * h->npad; c.x_out = w + W_XOUT * h->npad;
     c.hook_in = w + W_HIN * h->npad; c.hook_out = w + W_HOUT * h->npad;
     for (int i = 0; i < kNumVec; ++i) c.vec[i] = w + (W_VEC0 + i) * h->npad;
@@ -249,7 +269,7 @@ ccqp_status ccqp_destroy(ccqp_handle* h) {
     if (h->world > 1) ccqp_comm_detach(h);
     DevBuf* bufs[] = {&h->a_own, &h->lo, &h->hi, &h->ekind, &h->bkind, &h->boff, &h->bdim, &h->bpar, &h->small_ids,
                       &h->big_ids, &h->work, &h->partials, &h->flags, &h->out_dev, &h->uniforms,
-                      &h->batched_ws, &h->dbg};
+                      &h->batched_ws, &h->dbg, &h->ptr_own, &h->idx_own, &h->val_own};
     for (DevBuf* b : bufs) b->release();
     if (h->out_host) cudaFreeHost(h->out_host);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -272,7 +292,7 @@ ccqp_status ccqp_get_info(const ccqp_handle* h, int32_t* sm_count, int32_t* dens
     if (!h) return CCQP_ERR_INVALID_ARG;
     if (sm_count) *sm_count = h->sm_count;
     if (dense_threads) *dense_threads = kDenseThreads;
-    if (h->dA) {
+    if (h->have_matrix()) {
         Tiling t = choose_tiling(h);
         if (dense_grid) *dense_grid = t.grid;
         if (dense_smem_bytes) *dense_smem_bytes = (int64_t)t.smem;
@@ -289,6 +309,7 @@ ccqp_status ccqp_set_matrix(ccqp_handle* h, const double* A, int64_t n, int64_t 
         return CCQP_ERR_INVALID_ARG;
     CU(h, cudaSetDevice(h->device));
     h->n = n; h->row0 = row_begin; h->nrows = n_rows;
+    h->d_ptr = nullptr; h->d_idx = nullptr; h->d_val = nullptr; h->nnz = 0;
     if (memtype == CCQP_MEM_DEVICE) {
         h->dA = A; h->lda = lda;
     } else {
@@ -297,6 +318,34 @@ ccqp_status ccqp_set_matrix(ccqp_handle* h, const double* A, int64_t n, int64_t 
         CU(h, cudaMemcpy2DAsync(h->a_own.p, (size_t)ldd * 8, A, (size_t)lda * 8, (size_t)n * 8, (size_t)n_rows,
                                 cudaMemcpyHostToDevice, h->stream));
         h->dA = h->a_own.as<double>(); h->lda = ldd;
+    }
+    return CCQP_OK;
+}
+
+ccqp_status ccqp_set_matrix_csr(ccqp_handle* h, const int64_t* indptr, const int32_t* indices, const double* values,
+                                int64_t n, int64_t nnz, int64_t row_begin, int64_t n_rows, int memtype) {
+    if (!h || !indptr || n <= 0 || n >= (1LL << 31) - 256 || nnz < 0 || (nnz > 0 && (!indices || !values)) || row_begin < 0 ||
+        n_rows <= 0 || row_begin + n_rows > n)
+        return CCQP_ERR_INVALID_ARG;
+    CU(h, cudaSetDevice(h->device));
+    h->n = n; h->row0 = row_begin; h->nrows = n_rows; h->nnz = nnz;
+    h->dA = nullptr; h->lda = 0;
+    if (memtype == CCQP_MEM_DEVICE) {
+        h->d_ptr = reinterpret_cast<const long long*>(indptr); h->d_idx = indices; h->d_val = values;
+    } else {
+        if (indptr[0] != 0 || indptr[n_rows] != nnz) return CCQP_ERR_INVALID_ARG;
+        for (int64_t r = 0; r < n_rows; ++r) if (indptr[r + 1] < indptr[r]) return CCQP_ERR_INVALID_ARG;
+        for (int64_t q = 0; q < nnz; ++q) if (indices[q] < 0 || indices[q] >= n) return CCQP_ERR_INVALID_ARG;
+        CU(h, h->ptr_own.ensure((size_t)(n_rows + 1) * 8));
+        CU(h, h->idx_own.ensure((size_t)std::max<int64_t>(nnz, 1) * 4));
+        CU(h, h->val_own.ensure((size_t)std::max<int64_t>(nnz, 1) * 8));
+        CU(h, cudaMemcpyAsync(h->ptr_own.p, indptr, (size_t)(n_rows + 1) * 8, cudaMemcpyHostToDevice, h->stream));
+        if (nnz) {
+            CU(h, cudaMemcpyAsync(h->idx_own.p, indices, (size_t)nnz * 4, cudaMemcpyHostToDevice, h->stream));
+            CU(h, cudaMemcpyAsync(h->val_own.p, values, (size_t)nnz * 8, cudaMemcpyHostToDevice, h->stream));
+        }
+        CU(h, cudaStreamSynchronize(h->stream));       // pageable host arrays may go away
+        h->d_ptr = h->ptr_own.as<long long>(); h->d_idx = h->idx_own.as<int>(); h->d_val = h->val_own.as<double>();
     }
     return CCQP_OK;
 }
@@ -367,7 +416,7 @@ ccqp_status ccqp_solve(ccqp_handle* h, int solver, const ccqp_params* params, co
                        const double* uniforms, int64_t n_uniforms, double* x_out, int memtype, ccqp_result* result) {
     if (!h || !b || !x_out || !result || !params_ok(params, solver) || solver < 0 || solver > CCQP_SOLVER_MPRGP)
         return CCQP_ERR_INVALID_ARG;
-    if (!h->dA || !h->have_proj) return CCQP_ERR_NOT_READY;
+    if (!h->have_matrix() || !h->have_proj) return CCQP_ERR_NOT_READY;
     if (h->proj_n != h->n) return CCQP_ERR_INVALID_ARG;
     const bool sharded = h->world > 1;
     if (!sharded && (h->row0 != 0 || h->nrows != h->n)) return CCQP_ERR_UNSUPPORTED;   // a shard needs ccqp_comm_attach
@@ -448,7 +497,8 @@ ccqp_status ccqp_solve(ccqp_handle* h, int solver, const ccqp_params* params, co
     result->uniforms_used = o->draws;
     result->converged = o->converged;
     result->status = o->status;
-    result->hbm_bytes = (double)o->gemv * (8.0 * (double)h->nrows * (double)n + 8.0 * (double)n + 8.0 * (double)h->nrows);
+    result->hbm_bytes = h->d_val ? (double)o->gemv * (12.0 * (double)h->nnz + 8.0 * (double)(h->nrows + 1) + 8.0 * (double)n + 8.0 * (double)h->nrows)
+                                 : (double)o->gemv * (8.0 * (double)h->nrows * (double)n + 8.0 * (double)n + 8.0 * (double)h->nrows);
     result->kernel_launches = h->launches - launches0;
     return (ccqp_status)o->status;
 }
@@ -457,10 +507,10 @@ static ccqp_status run_hook(ccqp_handle* h, int op, const double* in, double* ou
                             int memtype) {
     if (!h || !in || !out) return CCQP_ERR_INVALID_ARG;
     CU(h, cudaSetDevice(h->device));
-    if (op == OP_GEMV) { if (!h->dA) return CCQP_ERR_NOT_READY; }
+    if (op == OP_GEMV) { if (!h->have_matrix()) return CCQP_ERR_NOT_READY; }
     else {
         if (!h->have_proj) return CCQP_ERR_NOT_READY;
-        if (!h->dA) { h->n = h->proj_n; h->row0 = 0; h->nrows = h->proj_n; }   // projection-only use
+        if (!h->have_matrix()) { h->n = h->proj_n; h->row0 = 0; h->nrows = h->proj_n; }   // projection-only use
         else if (h->proj_n != h->n) return CCQP_ERR_INVALID_ARG;
     }
     ccqp_status st = ensure_work(h);
@@ -471,7 +521,7 @@ static ccqp_status run_hook(ccqp_handle* h, int op, const double* in, double* ou
     CU(h, cudaMemsetAsync(w + W_HIN * npad, 0, (size_t)2 * npad * 8, h->stream));
     if ((st = copy_in(h, w + W_HIN * npad, in, n_in, memtype)) != CCQP_OK) return st;
     Tiling t;
-    if (h->dA) t = choose_tiling(h);
+    if (h->have_matrix()) t = choose_tiling(h);
     else { t.grid = (int)std::max<long long>(1, std::min<long long>(h->sm_count, h->n)); t.CW = 128; t.SW = 128; t.np = 1; t.nseg = 1; t.rows_max = 1; t.smem = dense_smem_bytes(128, 1, 1); }
     DenseCtx c;
     fill_ctx(h, c, t);
@@ -490,7 +540,7 @@ ccqp_status ccqp_gemv(ccqp_handle* h, const double* v, double* y, int memtype) {
 }
 ccqp_status ccqp_gemv_timed(ccqp_handle* h, const double* v_dev, double* y_dev, int repeats, double* seconds) {
     if (!h || !v_dev || !y_dev || repeats <= 0 || !seconds) return CCQP_ERR_INVALID_ARG;
-    if (!h->dA) return CCQP_ERR_NOT_READY;
+    if (!h->have_matrix()) return CCQP_ERR_NOT_READY;
     CU(h, cudaSetDevice(h->device));
     ccqp_status st = ensure_work(h);
     if (st != CCQP_OK) return st;

@@ -38,6 +38,7 @@ constexpr int kDenseThreads = CCQP_DENSE_THREADS;
 constexpr int kDenseWarps = kDenseThreads / 32;
 constexpr int kUnroll = CCQP_UNROLL;  // 256-bit loads in flight per lane
 constexpr int kMaxWindow = 64;        // SPG non-monotone window
+constexpr int kCsrUnroll = 16;        // CSR mat-vec: stored entries per lane in flight
 
 enum DenseOp : int {
     OP_PGD = 0, OP_APGD = 1, OP_APGD_AR = 2, OP_BBPGD = 3, OP_BBPGDF = 4, OP_SPG = 5, OP_MPRGP = 6,
@@ -59,6 +60,11 @@ struct DenseCtx {
     int n;              // columns = unknowns
     int row0, nrows;    // rows [row0, row0+nrows) live on this device
     int aligned;        // 256-bit path usable (A base and lda*8 multiples of 32 bytes)
+    // operator-form Hessian (CSR) instead of the dense rows: csr_val != nullptr
+    const long long* csr_ptr;   // [nrows + 1], relative to this shard (csr_ptr[0] = 0)
+    const int* csr_idx;         // [nnz] column indices
+    const double* csr_val;      // [nnz]
+    int csr_group;              // lanes that share one row: 2, 4, 8, 16 or 32 (from the mean row length)
     const double* b;    // [npad]
     const double* x0;   // [npad] (zeros if the caller passed none)
     ProjTable T;
@@ -225,10 +231,58 @@ __device__ __forceinline__ double dot_seg_generic(const double* __restrict__ aro
     return a0 + a1;
 }
 
+// CSR mat-vec phase (operator-form A: contact-style Hessians D^T M^-1 D are sparse).  A group of
+// csr_group lanes owns a row at a time: values and column indices are streamed coalesced (12 bytes
+// per stored entry, the HBM traffic of the phase), the entries of v are gathered from L2 (ld.cg: v
+// was written by other CTAs earlier in this kernel).  Fixed lane order + shuffle tree => deterministic.
+template <class Epi>
+__device__ __forceinline__ void gemv_phase_csr(Kst& k, const DenseCtx& c, const double* v, Epi epi) {
+    const int G = c.csr_group, glane = threadIdx.x & (G - 1), gid = threadIdx.x / G, ngroups = kDenseThreads / G;
+    const int nrows_cta = k.r1 - k.r0;
+    const int trips = (nrows_cta + ngroups - 1) / ngroups;          // uniform over the warp: shuffles below
+    for (int it = 0; it < trips; ++it) {
+        const int lr = it * ngroups + gid;
+        const bool valid = lr < nrows_cta;
+        const int row = k.r0 + lr;
+        long long p0 = 0, p1 = 0;
+        if (valid) { p0 = c.csr_ptr[row - c.row0]; p1 = c.csr_ptr[row - c.row0 + 1]; }
+        // kCsrUnroll stored entries per lane in flight: all column ids and values first, then all gathers, then
+        // the FMAs (the gather depends on the column id, so a short loop would serialise two memory latencies
+        // per entry; with 8 warps per SM the loop needs the instruction-level parallelism)
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        for (long long base = p0 + glane; base < p1; base += (long long)kCsrUnroll * G) {
+            int j[kCsrUnroll];
+            double w[kCsrUnroll], x[kCsrUnroll];
+#pragma unroll
+            for (int u = 0; u < kCsrUnroll; ++u) {
+                const long long q = base + (long long)u * G;
+                const bool ok = q < p1;
+                j[u] = ok ? __ldg(c.csr_idx + q) : 0;
+                w[u] = ok ? ldg_stream(c.csr_val + q) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < kCsrUnroll; ++u) x[u] = ld_cg(v + j[u]);
+#pragma unroll
+            for (int u = 0; u < kCsrUnroll; u += 4) {
+                a0 = fma(w[u], x[u], a0);
+                a1 = fma(w[u + 1], x[u + 1], a1);
+                a2 = fma(w[u + 2], x[u + 2], a2);
+                a3 = fma(w[u + 3], x[u + 3], a3);
+            }
+        }
+        double acc = (a0 + a1) + (a2 + a3);
+        for (int o = G >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (valid && glane == 0) epi(row, acc);
+    }
+    k.gemv += 1;
+    __syncthreads();
+}
+
 // y_row = sum_j A[row][j] v[j] for the rows of this CTA; epi(row, y_row) is called once per row.
 // v: full-length global vector (npad entries, zero tail), complete before the phase starts.
 template <class Epi>
 __device__ __forceinline__ void gemv_phase(Kst& k, const DenseCtx& c, const double* v, Epi epi) {
+    if (c.csr_val) { gemv_phase_csr(k, c, v, epi); return; }
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = c.n, CW = c.CW, SW = c.SW, np = c.np, nseg = c.nseg;
     const int nrows_cta = k.r1 - k.r0;

@@ -36,6 +36,39 @@ def _is_torch(a):
     return a is not None and not isinstance(a, np.ndarray) and hasattr(a, "data_ptr")
 
 
+def _is_sparse(a):
+    """scipy.sparse matrix / array, or a torch sparse-CSR tensor: the operator-form Hessians the reference can take
+    through `A.dot` (solvers.py:133)."""
+    if _is_torch(a) or hasattr(a, "layout"):
+        return str(getattr(a, "layout", "")) == "torch.sparse_csr"
+    return hasattr(a, "tocsr") and hasattr(a, "nnz")
+
+
+def _set_sparse_matrix(h, A, n):
+    """CSR arrays of A -> ccqp_set_matrix_csr.  Returns objects that must stay alive during the solve."""
+    lib = h.lib
+    if hasattr(A, "layout"):                                  # torch.sparse_csr
+        import torch
+        ptr = A.crow_indices().to(torch.int64).contiguous()
+        idx = A.col_indices().to(torch.int32).contiguous()
+        val = A.values().to(torch.float64).contiguous()
+        mem = _capi.MEM_DEVICE if val.is_cuda else _capi.MEM_HOST
+        keep = (ptr, idx, val)
+        args = (ptr.data_ptr(), idx.data_ptr(), val.data_ptr(), int(val.numel()))
+    else:
+        csr = A.tocsr()
+        csr.sum_duplicates()
+        ptr = np.ascontiguousarray(csr.indptr, dtype=np.int64)
+        idx = np.ascontiguousarray(csr.indices, dtype=np.int32)
+        val = np.ascontiguousarray(csr.data, dtype=np.float64)
+        mem = _capi.MEM_HOST
+        keep = (ptr, idx, val)
+        args = (ptr.ctypes.data, idx.ctypes.data, val.ctypes.data, int(val.size))
+    _capi.check(h.h, lib.ccqp_set_matrix_csr(h.h, ctypes.c_void_p(args[0]), ctypes.c_void_p(args[1]), ctypes.c_void_p(args[2]),
+                                              n, args[3], 0, n, mem))
+    return keep
+
+
 def _as_f64(a, like_device=None):
     """float64, C-contiguous view/copy of a NumPy array or torch tensor (README passes int64)."""
     if _is_torch(a):
@@ -45,8 +78,8 @@ def _as_f64(a, like_device=None):
             t = t.to(like_device)
         return t
     if hasattr(a, "dot") and not hasattr(a, "__array__"):
-        raise TypeError("A must be a dense array or tensor: the B200 path streams A from HBM and has no "
-                        "CPU fallback for operator-form matrices")
+        raise TypeError("A must be a dense array / tensor or a sparse (CSR-convertible) matrix: arbitrary objects that "
+                        "only offer .dot cannot run inside the CUDA solver and there is no CPU fallback")
     arr = np.ascontiguousarray(a, dtype=np.float64)
     if like_device is not None:
         import torch
@@ -125,27 +158,31 @@ class CCQPSolverBase(ABC):
         if not self.quiet:
             print("solving " + self._label)
 
-        on_device = _is_torch(A) and A.is_cuda
+        sparse = _is_sparse(A)
+        on_device = (_is_torch(A) or hasattr(A, "layout")) and A.is_cuda
         dev = A.device if on_device else None
         if on_device:
             device = A.device.index if A.device.index is not None else -1
-        A64 = _as_f64(A)
+        A64 = None if sparse else _as_f64(A)
         # the vectors live where A lives (or where b lives, if only b is a CUDA tensor)
         vec_dev = dev if on_device else (b.device if (_is_torch(b) and b.is_cuda) else None)
         b64 = _as_f64(b, vec_dev)
         x064 = None if x0 is None else _as_f64(x0, vec_dev)
-        if tuple(A64.shape) != (num_unknowns, num_unknowns):
+        if tuple(A.shape if sparse else A64.shape) != (num_unknowns, num_unknowns):
             raise ValueError("A must be (n, n) with n = b.shape[0]")
 
         h = _capi.default_handle(device)
         lib = h.lib
         if on_device or vec_dev is not None:
             import torch
-            with torch.cuda.device(A64.device if on_device else vec_dev):
+            with torch.cuda.device(dev if on_device else vec_dev):
                 _capi.check(h.h, lib.ccqp_set_stream(h.h, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
-        pa, mem_a, _ka = _capi.f64_ptr(A64)
-        lda = A64.stride(0) if _is_torch(A64) else num_unknowns
-        _capi.check(h.h, lib.ccqp_set_matrix(h.h, pa, num_unknowns, lda, 0, num_unknowns, mem_a))
+        if sparse:
+            _ka = _set_sparse_matrix(h, A, num_unknowns)
+        else:
+            pa, mem_a, _ka = _capi.f64_ptr(A64)
+            lda = A64.stride(0) if _is_torch(A64) else num_unknowns
+            _capi.check(h.h, lib.ccqp_set_matrix(h.h, pa, num_unknowns, lda, 0, num_unknowns, mem_a))
         blocks, params, _rows = convex_proj_op.descriptor()
         pp, _, _kp = _capi.f64_ptr(params if params.size else np.zeros(1))
         _capi.check(h.h, lib.ccqp_set_projection(h.h, blocks.ptr, len(blocks), pp, params.size))

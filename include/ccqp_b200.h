@@ -133,6 +133,13 @@ ccqp_status ccqp_get_info(const ccqp_handle* h, int32_t* sm_count, int32_t* dens
 ccqp_status ccqp_set_matrix(ccqp_handle* h, const double* A, int64_t n, int64_t lda,
                             int64_t row_begin, int64_t n_rows, int memtype);
 
+/* Operator-form Hessian in CSR.  The reference accepts any `A` with a .dot (solvers.py:133), in particular
+ * scipy.sparse matrices (contact-style Hessians D^T M^-1 D are sparse); this is that case.  indptr has
+ * n_rows + 1 entries RELATIVE to the shard (indptr[0] = 0, indptr[n_rows] = nnz), indices are column ids
+ * in [0, n).  DEVICE arrays are borrowed, HOST arrays are copied.  Replaces a previous ccqp_set_matrix(). */
+ccqp_status ccqp_set_matrix_csr(ccqp_handle* h, const int64_t* indptr, const int32_t* indices, const double* values,
+                                int64_t n, int64_t nnz, int64_t row_begin, int64_t n_rows, int memtype);
+
 /* The feasible set.  Replaces the `convex_proj_op` argument of solve() (solvers.py:94) and the
  * operator classes of solution_spaces.py.  blocks must tile [0,n) in order.  Host pointers. */
 ccqp_status ccqp_set_projection(ccqp_handle* h, const ccqp_block* blocks, int64_t n_blocks,
