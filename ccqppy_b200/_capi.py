@@ -21,7 +21,7 @@ ERR_UNIFORMS_EXHAUSTED = 7
 ERR_RANGE = 8
 
 EXPORTS = ["ccqp_abi_version", "ccqp_status_string", "ccqp_last_error", "ccqp_create", "ccqp_destroy",
-           "ccqp_set_stream", "ccqp_get_info", "ccqp_set_matrix", "ccqp_set_matrix_csr", "ccqp_set_projection", "ccqp_solve",
+           "ccqp_set_stream", "ccqp_get_info", "ccqp_set_matrix", "ccqp_set_matrix_csr", "ccqp_set_projection", "ccqp_solve", "ccqp_solve_async", "ccqp_solve_wait",
            "ccqp_solve_batched", "ccqp_gemv", "ccqp_gemv_timed", "ccqp_project", "ccqp_normal", "ccqp_comm_export",
            "ccqp_comm_attach", "ccqp_comm_prepare", "ccqp_comm_detach", "ccqp_debug_divide"]
 
@@ -76,6 +76,8 @@ def load():
     lib.ccqp_set_matrix_csr.argtypes = [vp, dp, dp, dp, i64, i64, i64, i64, i32]
     lib.ccqp_set_projection.argtypes = [vp, C.POINTER(Block), i64, dp, i64]
     lib.ccqp_solve.argtypes = [vp, i32, C.POINTER(Params), dp, dp, dp, i64, dp, i32, C.POINTER(Result)]
+    lib.ccqp_solve_async.argtypes = [vp, i32, C.POINTER(Params), dp, dp, dp, i64, dp, i32]
+    lib.ccqp_solve_wait.argtypes = [vp, C.POINTER(Result)]
     lib.ccqp_solve_batched.argtypes = [vp, i32, C.POINTER(Params), i64, i64, dp, dp, dp, dp, dp, dp, i64, dp, i32,
                                        C.POINTER(Result), C.POINTER(Result)]
     lib.ccqp_gemv.argtypes = [vp, dp, dp, i32]

@@ -60,6 +60,10 @@ struct ccqp_handle {
     void* out_host = nullptr;   // pinned
     long long npad = 0;
     long long launches = 0;
+    // a solve enqueued by ccqp_solve_async() and not yet collected by ccqp_solve_wait()
+    bool pending = false, pending_dbg = false;
+    int pending_solver = 0;
+    long long pending_launches0 = 0;
     // row-sharded multi-GPU solves: peers' symmetric buffers mapped through CUDA IPC
     int world = 1, rank = 0;
     char* peer_base[kMaxWorld] = {nullptr};
@@ -412,10 +416,11 @@ ccqp_status ccqp_set_projection(ccqp_handle* h, const ccqp_block* blocks, int64_
     return CCQP_OK;
 }
 
-ccqp_status ccqp_solve(ccqp_handle* h, int solver, const ccqp_params* params, const double* b, const double* x0,
-                       const double* uniforms, int64_t n_uniforms, double* x_out, int memtype, ccqp_result* result) {
-    if (!h || !b || !x_out || !result || !params_ok(params, solver) || solver < 0 || solver > CCQP_SOLVER_MPRGP)
+ccqp_status ccqp_solve_async(ccqp_handle* h, int solver, const ccqp_params* params, const double* b, const double* x0,
+                             const double* uniforms, int64_t n_uniforms, double* x_out, int memtype) {
+    if (!h || !b || !x_out || !params_ok(params, solver) || solver < 0 || solver > CCQP_SOLVER_MPRGP)
         return CCQP_ERR_INVALID_ARG;
+    if (h->pending) return CCQP_ERR_NOT_READY;          // one solve in flight per handle
     if (!h->have_matrix() || !h->have_proj) return CCQP_ERR_NOT_READY;
     if (h->proj_n != h->n) return CCQP_ERR_INVALID_ARG;
     const bool sharded = h->world > 1;
@@ -459,6 +464,18 @@ ccqp_status ccqp_solve(ccqp_handle* h, int solver, const ccqp_params* params, co
     CU(h, cudaEventRecord(h->ev1, h->stream));
     CU(h, cudaMemcpyAsync(h->out_host, h->out_dev.p, sizeof(DenseOut), cudaMemcpyDeviceToHost, h->stream));
     if ((st = copy_out(h, x_out, c.x_out, n, memtype)) != CCQP_OK) return st;
+    h->pending = true; h->pending_solver = solver; h->pending_launches0 = launches0; h->pending_dbg = dbg_timing;
+    return CCQP_OK;
+}
+
+ccqp_status ccqp_solve_wait(ccqp_handle* h, ccqp_result* result) {
+    if (!h || !result) return CCQP_ERR_INVALID_ARG;
+    if (!h->pending) return CCQP_ERR_NOT_READY;
+    h->pending = false;
+    CU(h, cudaSetDevice(h->device));
+    const int solver = h->pending_solver;
+    const long long launches0 = h->pending_launches0, n = h->n;
+    const bool dbg_timing = h->pending_dbg;
     cudaError_t e = cudaStreamSynchronize(h->stream);
     if (e != cudaSuccess) {
         h->last_error = std::string("solver kernel: ") + cudaGetErrorString(e);
@@ -501,6 +518,14 @@ ccqp_status ccqp_solve(ccqp_handle* h, int solver, const ccqp_params* params, co
                                  : (double)o->gemv * (8.0 * (double)h->nrows * (double)n + 8.0 * (double)n + 8.0 * (double)h->nrows);
     result->kernel_launches = h->launches - launches0;
     return (ccqp_status)o->status;
+}
+
+ccqp_status ccqp_solve(ccqp_handle* h, int solver, const ccqp_params* params, const double* b, const double* x0,
+                       const double* uniforms, int64_t n_uniforms, double* x_out, int memtype, ccqp_result* result) {
+    if (!result) return CCQP_ERR_INVALID_ARG;
+    const ccqp_status st = ccqp_solve_async(h, solver, params, b, x0, uniforms, n_uniforms, x_out, memtype);
+    if (st != CCQP_OK) return st;
+    return ccqp_solve_wait(h, result);
 }
 
 static ccqp_status run_hook(ccqp_handle* h, int op, const double* in, double* out, long long n_in, long long n_out,

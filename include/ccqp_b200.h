@@ -154,6 +154,17 @@ ccqp_status ccqp_solve(ccqp_handle* h, int solver, const ccqp_params* params, co
                        const double* x0, const double* uniforms, int64_t n_uniforms, double* x_out,
                        int memtype, ccqp_result* result);
 
+/* The same solve split in two, so that a caller with several handles (each has its own stream) can
+ * overlap the host->device copy of the NEXT problem's Hessian with the solve of the current one:
+ * ccqp_solve_async() enqueues the input copies, the solver kernel and the result copies on the
+ * handle's stream and returns; ccqp_solve_wait() synchronises and fills `result`.  Host buffers
+ * (b, x0, uniforms, x_out, and a host matrix given to ccqp_set_matrix) must stay valid -- and be
+ * pinned, for the copies to be asynchronous -- until the wait.  One solve in flight per handle. */
+ccqp_status ccqp_solve_async(ccqp_handle* h, int solver, const ccqp_params* params, const double* b,
+                             const double* x0, const double* uniforms, int64_t n_uniforms, double* x_out,
+                             int memtype);
+ccqp_status ccqp_solve_wait(ccqp_handle* h, ccqp_result* result);
+
 /* Many small independent box-constrained QPs, one CTA per problem, whole solver loop on the
  * device.  Problem i is defined to equal
  *     CCQPSolverX(tol,max_mv).solve(A[i], b[i], x0[i], BoxProjOp(n, lb[i], ub[i]))

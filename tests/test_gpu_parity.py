@@ -296,3 +296,29 @@ def test_device_matrix_with_unaligned_rows(n):
     _capi.check(h.h, h.lib.ccqp_gemv(h.h, ctypes.c_void_p(v.ctypes.data), ctypes.c_void_p(y.ctypes.data), _capi.MEM_HOST))
     h.close()
     np.testing.assert_allclose(y, A @ v, rtol=1e-12, atol=1e-12)
+
+
+def test_pipelined_solves_equal_synchronous_solves():
+    """ccqp_solve_async / ccqp_solve_wait through SolvePipeline: same kernel, same answers, any order of completion."""
+    import torch
+    from ccqppy_b200.pipeline import SolvePipeline
+    from ccqppy_b200 import solvers
+    probs = []
+    for i, n in enumerate([700, 1500, 64, 1500, 2048]):
+        A, b = pr.shift_problem(n, 30 + i)
+        probs.append((torch.from_numpy(A).pin_memory(), torch.from_numpy(b).pin_memory(), pr.mixed_table(n), pr.spg_uniforms(i, 2000)))
+    for solver in (pr.SPG, pr.BBPGD, pr.MPRGP):
+        pipe = SolvePipeline(make_solver(solver, 1e-7, 2000), depth=2)
+        for A, b, tab, uni in probs:
+            pipe.submit(A, b, convex_proj_op=op_from_table(tab), uniforms=uni if solver == pr.SPG else None)
+        got = pipe.results()
+        pipe.close()
+        assert len(got) == len(probs)
+        for (A, b, tab, uni), r in zip(probs, got):
+            s = make_solver(solver, 1e-7, 2000)
+            s.solve(A, b, convex_proj_op=op_from_table(tab), uniforms=uni)
+            assert r.solution_num_matrix_vector_multiplications == s.solution_num_matrix_vector_multiplications
+            assert r.solution_converged == s.solution_converged and r.solution_residual == s.solution_residual
+            assert np.array_equal(np.asarray(r.solution), np.asarray(s.solution))
+    with pytest.raises(ValueError):
+        SolvePipeline(solvers.CCQPSolverSPG(1e-6, 100)).submit(probs[0][0], probs[0][1])
