@@ -120,21 +120,35 @@ class ShardedSolver:
         blocks, params, rows = self.op.descriptor()
         self.ranges = shard_rows(rows, n, self.world)
         r0, r1 = self.ranges[self.rank]
-        if row_range is not None:
-            if tuple(row_range) != (r0, r1):
-                raise ValueError("row_range %s does not match the block-aligned split %s" % (row_range, (r0, r1)))
-            shard = A
-        else:
-            shard = A[r0:r1]
-        if not (hasattr(shard, "is_cuda") and shard.is_cuda):
-            shard = torch.as_tensor(np.ascontiguousarray(shard, dtype=np.float64)).to(self.device)
-        self.shard = shard.to(dtype=torch.float64).contiguous()     # keeps the storage alive
         self.h = _capi.Handle(self.device.index)
         lib = self.h.lib
         stream = torch.cuda.current_stream(self.device).cuda_stream
         _capi.check(self.h.h, lib.ccqp_set_stream(self.h.h, ctypes.c_void_p(stream)))
-        _capi.check(self.h.h, lib.ccqp_set_matrix(self.h.h, ctypes.c_void_p(self.shard.data_ptr()), n,
-                                                  self.shard.stride(0), r0, r1 - r0, _capi.MEM_DEVICE))
+        if hasattr(A, "tocsr"):
+            # operator-form Hessian (scipy.sparse): this rank keeps rows [r0, r1) of the CSR arrays
+            if row_range is not None:
+                raise ValueError("a sparse A is given in full; the shard is sliced here")
+            csr = A.tocsr()[r0:r1]
+            csr.sum_duplicates()
+            self.shard = (torch.from_numpy(np.ascontiguousarray(csr.indptr, dtype=np.int64)).to(self.device),
+                          torch.from_numpy(np.ascontiguousarray(csr.indices, dtype=np.int32)).to(self.device),
+                          torch.from_numpy(np.ascontiguousarray(csr.data, dtype=np.float64)).to(self.device))
+            ptr, idx, val = self.shard
+            _capi.check(self.h.h, lib.ccqp_set_matrix_csr(self.h.h, ctypes.c_void_p(ptr.data_ptr()), ctypes.c_void_p(idx.data_ptr()),
+                                                          ctypes.c_void_p(val.data_ptr()), n, int(val.numel()), r0, r1 - r0,
+                                                          _capi.MEM_DEVICE))
+        else:
+            if row_range is not None:
+                if tuple(row_range) != (r0, r1):
+                    raise ValueError("row_range %s does not match the block-aligned split %s" % (row_range, (r0, r1)))
+                shard = A
+            else:
+                shard = A[r0:r1]
+            if not (hasattr(shard, "is_cuda") and shard.is_cuda):
+                shard = torch.as_tensor(np.ascontiguousarray(shard, dtype=np.float64)).to(self.device)
+            self.shard = shard.to(dtype=torch.float64).contiguous()     # keeps the storage alive
+            _capi.check(self.h.h, lib.ccqp_set_matrix(self.h.h, ctypes.c_void_p(self.shard.data_ptr()), n,
+                                                      self.shard.stride(0), r0, r1 - r0, _capi.MEM_DEVICE))
         pp, _, _keep = _capi.f64_ptr(params if params.size else np.zeros(1))
         _capi.check(self.h.h, lib.ccqp_set_projection(self.h.h, blocks.ptr, len(blocks), pp, params.size))
         if self.world > 1:

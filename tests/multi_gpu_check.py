@@ -90,6 +90,26 @@ def main():
                        mv_single=r_dev.solution_num_matrix_vector_multiplications, err=0.0, ok=good, gpu_ms=0.0, single_ms=0.0))
     runner.close()
 
+    # ---- operator-form (CSR) Hessian, rows of the CSR arrays sharded over the ranks
+    from test_gpu_sparse import contact_like            # well conditioned: the counts do not depend on the summation order
+    n = 3000
+    As, bs = contact_like(n, 6, seed=12)
+    tab = pr.mixed_table(n)
+    op = op_from_table(tab)
+    for solver in (pr.BBPGD, pr.SPG, pr.MPRGP):
+        uni = pr.spg_uniforms(4, 2000)
+        one = make_solver(solver, 1e-7, 2000)
+        one.solve(As, bs, convex_proj_op=op, uniforms=uni)
+        runner = ShardedSolver(make_solver(solver, 1e-7, 2000), As, op, rank, world, dev)
+        r = runner.solve(bs, uniforms=uni)
+        err = float(np.linalg.norm(r.solution.cpu().numpy() - np.asarray(one.solution)) / np.linalg.norm(np.asarray(one.solution)))
+        good = r.solution_num_matrix_vector_multiplications == one.solution_num_matrix_vector_multiplications and err < 1e-9
+        ok = ok and good
+        report.append(dict(table="csr", solver=pr.SOLVER_NAMES[solver], mv=r.solution_num_matrix_vector_multiplications,
+                           mv_single=one.solution_num_matrix_vector_multiplications, err=err, ok=good,
+                           gpu_ms=1e3 * r.solution_gpu_time, single_ms=1e3 * one.solution_gpu_time))
+        runner.close()
+
     # ---- batched mode split over the ranks (no communication on the data path) against one GPU
     batch, nb = 37, 64
     Ab = np.empty((batch, nb, nb)); bb = np.empty((batch, nb))
