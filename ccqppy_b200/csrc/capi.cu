@@ -163,6 +163,8 @@ void fill_ctx(ccqp_handle* h, DenseCtx& c, const Tiling& t) {
         // flight per lane), so a lane should own tens of entries (sweep: tools/bench_sparse.py with CCQP_CSR_GROUP)
         c.csr_group = mean >= 1024 ? 32 : mean >= 512 ? 16 : mean >= 256 ? 8 : mean >= 128 ? 4 : 2;
         if (const char* e = getenv("CCQP_CSR_GROUP")) c.csr_group = atoi(e);
+        c.csr_l1 = 1;
+        if (const char* e = getenv("CCQP_CSR_L1")) c.csr_l1 = atoi(e);
     }
     c.b = w + W_B * h->npad; c.x0 = w + W_X0 * h->npad; c.x_out = w + W_XOUT * h->npad;
     c.hook_in = w + W_HIN * h->npad; c.hook_out = w + W_HOUT * h->npad;

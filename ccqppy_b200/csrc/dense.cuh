@@ -65,6 +65,7 @@ struct DenseCtx {
     const int* csr_idx;         // [nnz] column indices
     const double* csr_val;      // [nnz]
     int csr_group;              // lanes that share one row: 2, 4, 8, 16 or 32 (from the mean row length)
+    int csr_l1;                 // gather v through L1 (see ld_ca)
     const double* b;    // [npad]
     const double* x0;   // [npad] (zeros if the caller passed none)
     ProjTable T;
@@ -261,7 +262,7 @@ __device__ __forceinline__ void gemv_phase_csr(Kst& k, const DenseCtx& c, const 
                 w[u] = ok ? ldg_stream(c.csr_val + q) : 0.0;
             }
 #pragma unroll
-            for (int u = 0; u < kCsrUnroll; ++u) x[u] = ld_cg(v + j[u]);
+            for (int u = 0; u < kCsrUnroll; ++u) x[u] = c.csr_l1 ? ld_ca(v + j[u]) : ld_cg(v + j[u]);
 #pragma unroll
             for (int u = 0; u < kCsrUnroll; u += 4) {
                 a0 = fma(w[u], x[u], a0);

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define CCQP_ABI_VERSION 1
+#define CCQP_ABI_VERSION 2
 
 typedef enum ccqp_status {
     CCQP_OK = 0,
@@ -129,7 +129,9 @@ ccqp_status ccqp_get_info(const ccqp_handle* h, int32_t* sm_count, int32_t* dens
 /* The Hessian.  Replaces the `A` argument of solve() (solvers.py:94); the reference touches A
  * only through A.dot(v) (26 call sites).  `A` points at rows
  * [row_begin, row_begin+n_rows) of the n x n matrix (row shard; single GPU: row_begin = 0,
- * n_rows = n).  A DEVICE matrix is borrowed, not copied, and must outlive the solves.      */
+ * n_rows = n).  A DEVICE matrix is borrowed, not copied, and must outlive the solves.  A HOST
+ * matrix is copied on the handle's stream: from pinned memory that copy is asynchronous, so the
+ * buffer must stay valid until the next ccqp_solve() / ccqp_solve_wait() on the handle returns. */
 ccqp_status ccqp_set_matrix(ccqp_handle* h, const double* A, int64_t n, int64_t lda,
                             int64_t row_begin, int64_t n_rows, int memtype);
 
