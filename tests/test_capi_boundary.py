@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
     lib = _capi.load()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.ccqp_abi_version() == 1
+    assert lib.ccqp_abi_version() == 2
     assert lib.ccqp_status_string(0) == b"ok"
     assert b"Cone normal" in lib.ccqp_status_string(6)
 
