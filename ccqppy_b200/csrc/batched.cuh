@@ -184,6 +184,19 @@ __device__ __forceinline__ void cta64_sum(double (&a)[K], const BShared& sh, int
     parity ^= 1;
 }
 
+// bitwise AND of a 64-bit mask over the 64 threads (MPRGP's bisection); ONE __syncthreads
+__device__ __forceinline__ unsigned long long cta64_and(unsigned long long m, const BShared& sh, int& parity) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    m = warp_and64(m);
+    const uint32_t base = sh.red + (uint32_t)parity * 64u;
+    if (lane == 0) sts_f64(base + (uint32_t)warp * 32u, __longlong_as_double((long long)m));
+    __syncthreads();
+    const unsigned long long r = (unsigned long long)__double_as_longlong(lds_f64(base)) &
+                                 (unsigned long long)__double_as_longlong(lds_f64(base + 32));
+    parity ^= 1;
+    return r;
+}
+
 __device__ __forceinline__ double clampd(double t, double lo, double hi) { return t < lo ? lo : (t > hi ? hi : t); }
 
 // Publish v (entry t of the mat-vec input) and return (A v)_t.
@@ -425,6 +438,109 @@ __device__ __forceinline__ void solve_one(const BatchedCtx& c, const double (&a)
         }
         res = sqrt(res2);
         xsol = AR ? xhat : xp;
+    } else if constexpr (SOLVER == CCQP_SOLVER_MPRGP) {
+        // solvers.py:1048-1200 with the Box operator of solution_spaces.py:280-366; statement by statement the
+        // dense program (dense.cuh solve_mprgp) with one unknown per thread
+        auto feas = [&](double v) { return is_close(v, clampd(v, s.lo, s.hi)); };
+        double xk = clampd(s.x0, s.lo, s.hi), xn = xk;
+        double gk = matvec(a, sm, xpar, s.act, xk) + s.b, gn = gk; gemv++; mv = 1;
+        double r1[1] = {resid2(xk, gk)};
+        cta64_sum<1>(r1, sm, par);
+        double res2 = r1[0];
+        if (!(res2 < c.thr_lt)) {
+            const double ag = matvec(a, sm, xpar, s.act, gk); gemv++; mv++;       // counted (:1077-1078)
+            double q2[2] = {gk * ag, gk * gk};
+            cta64_sum<2>(q2, sm, par);
+            double abb = q2[1] / q2[0];
+            bool abb_lazy = false;                      // true: abb = BB(xk - xn) still to be evaluated
+            double p = feas(xk) ? gk : 0.0, Ap = 0.0;
+            for (;;) {
+                gk = matvec(a, sm, xpar, s.act, xk) + s.b; gemv++; mv++;
+                if (mv >= maxmv) break;
+                const bool cl = feas(xk);                                          // delta (:1093)
+                const double psi = cl ? gk : 0.0;
+                double q3[3] = {psi * psi, psi * p, (cl || !s.act) ? 0.0 : 1.0};
+                cta64_sum<3>(q3, sm, par);
+                double betbet = 0.0;
+                if (q3[2] > 0.0) {
+                    // some entry is not (close to) feasible: normal_vector of the Box (:306-322) and the GLOBAL n.g
+                    const double px = clampd(xk, s.lo, s.hi), dx = xk - px;
+                    double d1[1] = {dx * dx};
+                    cta64_sum<1>(d1, sm, par);
+                    double nv = 0.0;
+                    if (s.act && is_close(sqrt(d1[0]), 0.0)) nv = is_close(px, s.hi) ? 1.0 : (is_close(px, s.lo) ? -1.0 : 0.0);
+                    double s1[1] = {nv * gk};
+                    cta64_sum<1>(s1, sm, par);
+                    const double mng = s1[0] < 0.0 ? s1[0] : 0.0;                  // np.min([0, n.g])
+                    const double bv = ((cl || !s.act) ? 0.0 : 1.0) * (gk - mng * nv);
+                    double s2[1] = {bv * bv};
+                    cta64_sum<1>(s2, sm, par);
+                    betbet = s2[0];
+                }
+                if (betbet < q3[0]) {
+                    Ap = matvec(a, sm, xpar, s.act, p); gemv++; mv++;
+                    double s1[1] = {p * Ap};
+                    cta64_sum<1>(s1, sm, par);
+                    if (mv >= maxmv) break;
+                    const double pAp = s1[0];
+                    const double acg = q3[1] / pAp;
+                    double af = acg + 10 * kEps;
+                    for (int pass = 0;; ++pass) {                                  // feasibility bisection :1112-1118
+                        unsigned long long m = ~0ull;
+                        if (s.act) {
+                            double al = af;
+                            for (int j = 0; j < 64; ++j, al *= 0.5) if (!feas(xk - al * p)) m &= ~(1ull << j);
+                        }
+                        m = cta64_and(m, sm, par);
+                        if (m) { const int j = __ffsll((long long)m) - 1; for (int q = 0; q < j; ++q) af *= 0.5; break; }
+                        for (int q = 0; q < 64; ++q) af *= 0.5;
+                        if (pass >= 20) break;
+                    }
+                    if (acg <= af) {                                               // conjugate-gradient step :1121-1135
+                        const double yv = xk - acg * p;
+                        const double gni = gk - acg * Ap;
+                        xn = yv; gn = gni;
+                        const double psy = feas(yv) ? gni : 0.0;
+                        const double bet = psy * Ap / pAp;                         // elementwise "beta" (:1134)
+                        p = psy - bet * p;
+                        abb_lazy = true;
+                    } else {                                                       // expansion step :1136-1163
+                        const double xh = xk - af * p, gh = gk - af * Ap;
+                        const double sx = xh - xk, sg = gh - gk;
+                        double s2[2] = {sx * sx, sx * sg};
+                        cta64_sum<2>(s2, sm, par);
+                        const double al = s2[0] / (s2[1] + 10 * kEps);
+                        xn = clampd(xh - al * gh, s.lo, s.hi);
+                        gn = matvec(a, sm, xpar, s.act, xn) + s.b; gemv++; mv++;
+                        if (mv >= maxmv) break;
+                        p = feas(xn) ? gn : 0.0;
+                        abb_lazy = true;
+                    }
+                } else {                                                           // proportioning step :1164-1182
+                    if (abb_lazy) {
+                        const double w = xk - xn;
+                        const double Aw = matvec(a, sm, xpar, s.act, w); gemv++;  // not counted (:1129,:1163,:1172)
+                        double s2[2] = {w * w, w * Aw};
+                        cta64_sum<2>(s2, sm, par);
+                        abb = s2[0] / (s2[1] + 10 * kEps);
+                    }
+                    xn = clampd(xk - abb * gk, s.lo, s.hi);
+                    abb_lazy = true;
+                    mv++;                    // gk = A xk + b is re-evaluated by the reference (:1174); same value
+                    if (mv >= maxmv) break;
+                    p = feas(xn) ? gn : 0.0;                                       // stale gn (:1181)
+                }
+                double r2[1] = {resid2(xn, gn)};
+                cta64_sum<1>(r2, sm, par);
+                res2 = r2[0];
+                iters++;
+                if (res2 < c.thr_lt) break;
+                { const double t = xk; xk = xn; xn = t; }
+                { const double t = gk; gk = gn; gn = t; }
+            }
+        }
+        res = sqrt(res2);
+        xsol = xn;
     }
     o.residual = res;
     o.mv = mv; o.gemv = gemv; o.iters = iters; o.draws = draws;
@@ -594,7 +710,6 @@ inline int batched_solve(cudaStream_t stream, int sm_count, void*, size_t, int s
 #define BCU(call)                                                                                  \
     do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { err = std::string(#call) + ": " + cudaGetErrorString(e__); return CCQP_ERR_CUDA; } } while (0)
     if (n > kBN) return CCQP_ERR_UNSUPPORTED;
-    if (solver == CCQP_SOLVER_MPRGP) return CCQP_ERR_UNSUPPORTED;
     if (batch >= (1LL << 31) - 1024) return CCQP_ERR_INVALID_ARG;
     const bool host = memtype == CCQP_MEM_HOST;
     if (solver == CCQP_SOLVER_SPG && (n_uniforms < 0 || (n_uniforms > 0 && !uniforms))) return CCQP_ERR_INVALID_ARG;
@@ -653,6 +768,7 @@ inline int batched_solve(cudaStream_t stream, int sm_count, void*, size_t, int s
         case CCQP_SOLVER_APGD_AR: le = launch_batched<CCQP_SOLVER_APGD_AR, true>(c, sm_count, stream); break;
         case CCQP_SOLVER_BBPGD: le = launch_batched<CCQP_SOLVER_BBPGD, true>(c, sm_count, stream); break;
         case CCQP_SOLVER_BBPGDF: le = launch_batched<CCQP_SOLVER_BBPGDF, true>(c, sm_count, stream); break;
+        case CCQP_SOLVER_MPRGP: le = launch_batched<CCQP_SOLVER_MPRGP, true>(c, sm_count, stream); break;
         case CCQP_SOLVER_SPG:
             le = wreg ? launch_batched<CCQP_SOLVER_SPG, true>(c, sm_count, stream)
                       : launch_batched<CCQP_SOLVER_SPG, false>(c, sm_count, stream);

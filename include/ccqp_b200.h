@@ -172,7 +172,7 @@ ccqp_status ccqp_solve_wait(ccqp_handle* h, ccqp_result* result);
  *     CCQPSolverX(tol,max_mv).solve(A[i], b[i], x0[i], BoxProjOp(n, lb[i], ub[i]))
  * (solvers.py:94.. with solution_spaces.py:280).  A is [batch][n][n]; b, x0 (nullable), lb, ub,
  * x_out are [batch][n]; uniforms is [batch][n_uniforms] (SPG); results is [batch] in HOST memory.
- * Supported n: 1..64 (n = 64 is the tuned case). */
+ * Supported n: 1..64 (n = 64 is the tuned case); all seven solvers. */
 ccqp_status ccqp_solve_batched(ccqp_handle* h, int solver, const ccqp_params* params, int64_t batch,
                                int64_t n, const double* A, const double* b, const double* x0,
                                const double* lb, const double* ub, const double* uniforms,

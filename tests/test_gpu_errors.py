@@ -50,8 +50,8 @@ def test_status_codes_of_the_c_abi():
     v = np.zeros((3, 65))
     assert lib.ccqp_solve_batched(h.h, _capi.BBPGD, ctypes.byref(prm), 3, 65, P(big), P(v), None, P(v), P(v), None, 0, P(v),
                                   _capi.MEM_HOST, None, None) == 4        # n > 64
-    assert lib.ccqp_solve_batched(h.h, _capi.MPRGP, ctypes.byref(prm), 3, 8, P(big), P(v), None, P(v), P(v), None, 0, P(v),
-                                  _capi.MEM_HOST, None, None) == 4        # no batched MPRGP
+    assert lib.ccqp_solve_batched(h.h, 7, ctypes.byref(prm), 3, 8, P(big), P(v), None, P(v), P(v), None, 0, P(v),
+                                  _capi.MEM_HOST, None, None) == 1        # unknown solver
     h.close()
 
 
