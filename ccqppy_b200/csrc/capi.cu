@@ -127,7 +127,11 @@ struct Tiling { int grid, CW, SW, np, nseg, rows_max; size_t smem; };
 Tiling choose_tiling(const ccqp_handle* h) {
     Tiling t;
     const long long n = h->n, nrows = h->nrows;
-    t.grid = (int)std::max(1LL, std::min<long long>(h->sm_count, nrows));
+    // one CTA per SM, but never more CTAs than there is work for: a CTA should own at least 8K matrix entries
+    // (16K stored entries of a CSR matrix); tiny problems (the reference's own 3x3 tests) then run in ONE CTA,
+    // whose syncs are plain __syncthreads() (grid_xsync)
+    const long long work = h->d_val ? h->nnz / 16384 : (nrows * n) / 8192;
+    t.grid = (int)std::max(1LL, std::min<long long>(std::min<long long>(h->sm_count, nrows), std::max(1LL, work)));
     if (h->d_val) {     // CSR: no panels of the input vector in shared memory
         t.CW = 128; t.SW = 128; t.np = 1; t.nseg = 1; t.rows_max = 1;
         t.smem = dense_smem_bytes(t.CW, t.rows_max, t.nseg);

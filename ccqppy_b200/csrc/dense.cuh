@@ -167,7 +167,7 @@ __device__ __forceinline__ unsigned long long and_sync(Kst& k, const DenseCtx& c
     if (lane == 0) k.sm.ascratch[warp] = m;
     __syncthreads();
     unsigned long long v[1] = {~0ull};
-    if (threadIdx.x == 0) for (int w = 0; w < kDenseWarps; ++w) v[0] &= k.sm.ascratch[w];
+    for (int w = 0; w < kDenseWarps; ++w) v[0] &= k.sm.ascratch[w];      // every thread: a one-CTA solve returns these as they are
     grid_xsync<1, true>(c.gs, c.x, k.epoch, k.xepoch, false, v, reinterpret_cast<unsigned long long*>(k.sm.scratch));
     return v[0];
 }
