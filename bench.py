@@ -48,6 +48,28 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on the first
+# communicator), so the process's fd 1 is pointed at stderr for the whole run and the JSON line goes to the saved,
+# real stdout.
+_REAL_STDOUT = None
+
+
+def capture_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def measured_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -166,7 +188,7 @@ def run_reference_arm(args, rank):
                                          "reference" % (args.steps, REF_SAMPLE_MV, n)),
                 e2e=dict(value=value, unit="iterations/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 effective_GBps=value * (8.0 * n * n + 16.0 * n) / 1e9)
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -244,6 +266,7 @@ def main():
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    capture_stdout()
     if args.impl == "reference":
         run_reference_arm(args, rank)
         return
@@ -256,7 +279,6 @@ def main():
     device = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's banner / warnings off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=device)
     n = N_DENSE
     t_gen = time.time()
@@ -475,7 +497,7 @@ def main():
                            note="every solve re-uploads the Hessian: each rank copies its %d rows (%.2f GB) from pinned host "
                                 "memory over its own PCIe link" % (r1 - r0, 8e-9 * (r1 - r0) * n))
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
