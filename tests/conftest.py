@@ -23,6 +23,15 @@ def _have_gpu():
 
 def pytest_collection_modifyitems(config, items):
     if _have_gpu():
+        # a persistent kernel that deadlocks cannot be interrupted from Python: if pytest-timeout is there, let it
+        # kill the process (method="thread" ends it with os._exit, which tears the CUDA context down)
+        try:
+            import pytest_timeout  # noqa: F401
+            for item in items:
+                if "gpu" in item.keywords and item.get_closest_marker("timeout") is None:
+                    item.add_marker(pytest.mark.timeout(600, method="thread"))
+        except ImportError:
+            pass
         return
     skip = pytest.mark.skip(reason="no CUDA device")
     for item in items:
