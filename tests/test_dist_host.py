@@ -77,3 +77,33 @@ def test_descriptor_exchange_gloo_world2():
     for p in procs:
         p.join(timeout=60)
     assert got == [(0, True), (1, True)]
+
+
+def test_split_properties_on_random_tables():
+    """Any table / world size: the ranges tile [0, n) in order, and no norm-type block is cut."""
+    hyp = pytest.importorskip("hypothesis")
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=200, deadline=None)
+    @given(seed=st.integers(0, 2 ** 31 - 1), world=st.integers(1, 8))
+    def check(seed, world):
+        rng = np.random.default_rng(seed)
+        t = pr.Table()
+        for _ in range(int(rng.integers(1, 60))):
+            kind = int(rng.integers(0, 7))
+            dim = int(rng.integers(1, 40))
+            if kind == pr.IDENTITY: t.add(kind, dim)
+            elif kind in (pr.LOWER, pr.UPPER): t.add(kind, dim, 0.0)
+            elif kind == pr.BOX: t.add(kind, dim, -1.0, 1.0)
+            else: t.add(kind, dim, 1.0)
+        try:
+            r = shard_rows(t.rows, t.n, world)
+        except ValueError:
+            return          # fewer cut points than ranks: refused, not mis-split
+        assert r[0][0] == 0 and r[-1][1] == t.n and len(r) == world
+        assert all(a[1] == b[0] and a[1] > a[0] for a, b in zip(r[:-1], r[1:])) and r[-1][1] > r[-1][0]
+        cuts = {a[1] for a in r[:-1]}
+        for kind, off, dim, _ in t.rows:
+            if kind in (pr.SPHERE, pr.CONE_REF, pr.SOC) and dim > 1:
+                assert not any(off < c < off + dim for c in cuts)
+    check()
