@@ -28,7 +28,8 @@ def main():
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     report, ok = [], True
-    cases = [("mixed", pr.mixed_table(1200), 1200, 1.0), ("box", pr.box_table(4096), 4096, 1.0),
+    cases = [("tiny", pr.box_table(40), 40, 1.0),      # one CTA per rank: local syncs are plain barriers, cross syncs are not
+             ("mixed", pr.mixed_table(1200), 1200, 1.0), ("box", pr.box_table(4096), 4096, 1.0),
              ("sphere3", pr.sphere3_table(1000), 1000, 1.0), ("box_odd", pr.box_table(1023), 1023, 0.3)]
     for tname, tab, n, mu in cases:
         A, b = pr.shift_problem(n, 5, mu)
