@@ -23,7 +23,8 @@ ERR_RANGE = 8
 EXPORTS = ["ccqp_abi_version", "ccqp_status_string", "ccqp_last_error", "ccqp_create", "ccqp_destroy",
            "ccqp_set_stream", "ccqp_get_info", "ccqp_set_matrix", "ccqp_set_matrix_csr", "ccqp_set_projection", "ccqp_solve", "ccqp_solve_async", "ccqp_solve_wait",
            "ccqp_solve_batched", "ccqp_gemv", "ccqp_gemv_timed", "ccqp_project", "ccqp_normal", "ccqp_comm_export",
-           "ccqp_comm_attach", "ccqp_comm_prepare", "ccqp_comm_detach", "ccqp_debug_divide"]
+           "ccqp_comm_attach", "ccqp_comm_prepare", "ccqp_comm_detach", "ccqp_debug_divide", "ccqp_fp64_peak",
+           "ccqp_microbench"]
 
 
 class Block(C.Structure):
@@ -85,6 +86,8 @@ def load():
     lib.ccqp_project.argtypes = [vp, dp, dp, i32]
     lib.ccqp_normal.argtypes = [vp, dp, dp, i32]
     lib.ccqp_debug_divide.argtypes = [vp, dp, dp, dp, dp, dp, dp, dp, i64]
+    lib.ccqp_fp64_peak.argtypes = [vp, i32, i32, C.POINTER(C.c_double)]
+    lib.ccqp_microbench.argtypes = [vp, C.POINTER(C.c_double), C.c_int32]
     lib.ccqp_comm_export.argtypes = [vp, i32, i32, i64, vp]
     lib.ccqp_comm_attach.argtypes = [vp, vp]
     lib.ccqp_comm_prepare.argtypes = [vp]
@@ -102,8 +105,12 @@ def check(handle, status):
         return
     lib = load()
     text = lib.ccqp_status_string(status).decode()
-    if status == 3 and handle:
-        text += ": " + lib.ccqp_last_error(handle).decode()
+    if status in (3, 4, 5, 10) and handle:
+        detail = lib.ccqp_last_error(handle).decode()
+        if detail:
+            text += ": " + detail
+    if status == 9:
+        text += " (the kernel trapped: this process's CUDA context is unusable from here on; restart the process)"
     raise CCQPError(status, text)
 
 
@@ -128,6 +135,21 @@ class Handle:
             self.close()
         except Exception:
             pass
+
+    def fp64_peak(self, blocks_per_sm=8, threads_per_block=256):
+        """Measured DFMA throughput of the device, TFLOP/s (ccqp_fp64_peak)."""
+        out = C.c_double()
+        check(self.h, self.lib.ccqp_fp64_peak(self.h, int(blocks_per_sm), int(threads_per_block), C.byref(out)))
+        return out.value
+
+    PROBES = ("dfma", "dadd", "dmul", "shfl64_dadd", "div_dadd", "sqrt_dadd", "lds128_bcast_dadd", "lds128_distinct_dadd",
+              "sts_bar_lds_dadd_bar", "bar64", "dsetp_sel_dadd")
+
+    def microbench(self):
+        """SM cycles per dependent operation (ccqp_microbench), as a dict."""
+        out = (C.c_double * len(self.PROBES))()
+        check(self.h, self.lib.ccqp_microbench(self.h, out, len(self.PROBES)))
+        return dict(zip(self.PROBES, [float(v) for v in out]))
 
     def info(self):
         sm, grid, thr, smem = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int64()

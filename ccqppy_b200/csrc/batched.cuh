@@ -544,7 +544,7 @@ __device__ __forceinline__ void solve_one(const BatchedCtx& c, const double (&a)
     }
     o.residual = res;
     o.mv = mv; o.gemv = gemv; o.iters = iters; o.draws = draws;
-    o.converged = (mv < maxmv) ? 1 : 0;
+    o.converged = (mv < maxmv && status == 0) ? 1 : 0;   // a problem that stopped on an error is not a converged one
     o.status = status;
 }
 

@@ -4,6 +4,7 @@
 // the result record back.  No algorithm runs on the CPU here.
 #include "../../include/ccqp_b200.h"
 
+#include <climits>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -14,6 +15,7 @@
 
 #include "batched.cuh"
 #include "dense.cuh"
+#include "microbench.cuh"
 
 using namespace ccqp;
 
@@ -68,6 +70,10 @@ struct ccqp_handle {
     int world = 1, rank = 0;
     char* peer_base[kMaxWorld] = {nullptr};
     bool comm_ready = false;
+    bool comm_prepared = false;     // ccqp_comm_prepare() ran since the last sharded solve (stale packets would match)
+    // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute of each kernel instantiation: one bit per
+    // instantiation, kept per handle (a handle owns exactly one device)
+    unsigned smem_attr_mask = 0;
 };
 
 namespace {
@@ -122,35 +128,73 @@ ccqp_status ensure_work(ccqp_handle* h) {
     return CCQP_OK;
 }
 
-struct Tiling { int grid, CW, SW, np, nseg, rows_max; size_t smem; };
+struct Tiling { int grid, CW, SW, np, nseg, rows_max, accum; size_t smem; };
+
+// Tuning overrides from the environment are accepted only when they are usable (a bad value is ignored, not obeyed)
+int env_int(const char* name, int fallback, bool (*ok)(int)) {
+    const char* e = getenv(name);
+    if (!e || !*e) return fallback;
+    char* end = nullptr;
+    const long v = strtol(e, &end, 10);
+    if (end == e || *end != 0 || v < INT_MIN || v > INT_MAX || !ok((int)v)) {
+        fprintf(stderr, "[ccqp] ignoring %s=%s (not a usable value)\n", name, e);
+        return fallback;
+    }
+    return (int)v;
+}
+bool ok_mult128(int v) { return v >= 128 && v % 128 == 0 && v <= 16384; }
+bool ok_csr_group(int v) { return v == 2 || v == 4 || v == 8 || v == 16 || v == 32; }
+bool ok_bool(int v) { return v == 0 || v == 1; }
 
 Tiling choose_tiling(const ccqp_handle* h) {
     Tiling t;
     const long long n = h->n, nrows = h->nrows;
-    // one CTA per SM, but never more CTAs than there is work for: a CTA should own at least 8K matrix entries
+    // One CTA per SM, but never more CTAs than there is work for: a CTA should own at least 8K matrix entries
     // (16K stored entries of a CSR matrix); tiny problems (the reference's own 3x3 tests) then run in ONE CTA,
-    // whose syncs are plain __syncthreads() (grid_xsync)
-    const long long work = h->d_val ? h->nnz / 16384 : (nrows * n) / 8192;
-    t.grid = (int)std::max(1LL, std::min<long long>(std::min<long long>(h->sm_count, nrows), std::max(1LL, work)));
+    // whose syncs are plain __syncthreads() (grid_xsync).
+    // Sharded solves: every rank must launch the SAME grid, because the elementwise reductions that every rank
+    // repeats on the full vectors are summed CTA by CTA (a different grid = a different summation order = scalars
+    // that differ in the last bit across ranks = ranks that may take different branches).  So the grid is derived
+    // from n and world only (the even split), never from this rank's own row count or nnz; a rank whose
+    // block-aligned shard has fewer rows than CTAs simply has some CTAs without rows (they still take part in
+    // the syncs and the elementwise passes).  All ranks of a box have the same SM count.
+    const bool sharded = h->world > 1;
+    const long long rows_ref = sharded ? std::max<long long>(1, n / h->world) : nrows;
+    const long long work = h->d_val ? (sharded ? rows_ref : h->nnz / 16384) : (rows_ref * n) / 8192;
+    t.grid = (int)std::max(1LL, std::min<long long>(std::min<long long>(h->sm_count, rows_ref), std::max(1LL, work)));
+    t.accum = 0;
     if (h->d_val) {     // CSR: no panels of the input vector in shared memory
         t.CW = 128; t.SW = 128; t.np = 1; t.nseg = 1; t.rows_max = 1;
         t.smem = dense_smem_bytes(t.CW, t.rows_max, t.nseg);
         return t;
     }
     t.rows_max = (int)((nrows + t.grid - 1) / t.grid) + 1;
-    t.CW = (int)std::min<long long>(8192, round_up(n, 128));
+    const int cw_cap = (int)round_up(n, 128);
+    t.CW = std::min(8192, cw_cap);
     t.SW = std::min(2048, t.CW);
     // tuning overrides (multiples of 128; SW must divide CW)
-    if (const char* e = getenv("CCQP_CW")) t.CW = (int)std::min<long long>(atoi(e), round_up(n, 128));
-    if (const char* e = getenv("CCQP_SW")) t.SW = std::min(atoi(e), t.CW);
-    for (;;) {
+    t.CW = std::min(env_int("CCQP_CW", t.CW, ok_mult128), cw_cap);
+    t.SW = std::min(env_int("CCQP_SW", t.SW, ok_mult128), t.CW);
+    if (t.CW % t.SW != 0) t.SW = t.CW;
+    const int sw0 = t.SW;
+    auto layout = [&]() {
         t.np = (int)((n + t.CW - 1) / t.CW);
         const int spp_full = t.CW / t.SW;
         const int last = (int)(n - (long long)(t.np - 1) * t.CW);
-        t.nseg = (t.np - 1) * spp_full + (last + t.SW - 1) / t.SW;
+        t.nseg = t.accum ? spp_full : (t.np - 1) * spp_full + (last + t.SW - 1) / t.SW;
         t.smem = dense_smem_bytes(t.CW, t.rows_max, t.nseg);
-        if (t.smem <= 200 * 1024 || t.SW >= t.CW) break;
+    };
+    for (;;) {
+        layout();
+        if (t.smem <= kDenseSmemTarget || t.SW >= t.CW) break;
         t.SW *= 2;   // fewer, wider segments when a CTA owns many rows of a very wide matrix
+    }
+    if (t.smem > kDenseSmemTarget) {
+        // very wide matrices (n beyond ~100k on one GPU): one partial sum per (row, segment of the whole row) no
+        // longer fits; keep one slot per (row, segment of a PANEL) and add the panels up in panel order instead
+        t.accum = 1;
+        t.SW = sw0;
+        layout();
     }
     return t;
 }
@@ -166,9 +210,8 @@ void fill_ctx(ccqp_handle* h, DenseCtx& c, const Tiling& t) {
         // few lanes per row: with 8 warps per SM the loop lives on instruction-level parallelism (16 entries in
         // flight per lane), so a lane should own tens of entries (sweep: tools/bench_sparse.py with CCQP_CSR_GROUP)
         c.csr_group = mean >= 1024 ? 32 : mean >= 512 ? 16 : mean >= 256 ? 8 : mean >= 128 ? 4 : 2;
-        if (const char* e = getenv("CCQP_CSR_GROUP")) c.csr_group = atoi(e);
-        c.csr_l1 = 1;
-        if (const char* e = getenv("CCQP_CSR_L1")) c.csr_l1 = atoi(e);
+        c.csr_group = env_int("CCQP_CSR_GROUP", c.csr_group, ok_csr_group);
+        c.csr_l1 = env_int("CCQP_CSR_L1", 1, ok_bool);
     }
     c.b = w + W_B * h->npad; c.x0 = w + W_X0 * h->npad; c.x_out = w + W_XOUT * h->npad;
     c.hook_in = w + W_HIN * h->npad; c.hook_out = w + W_HOUT * h->npad;
@@ -191,17 +234,22 @@ void fill_ctx(ccqp_handle* h, DenseCtx& c, const Tiling& t) {
     for (int s = 0; s < kMaxWorld; ++s) c.x.base[s] = (s < h->world) ? h->peer_base[s] : nullptr;
     if (h->world == 1) c.x.base[0] = h->work.as<char>();
     c.out = h->out_dev.as<DenseOut>();
-    c.CW = t.CW; c.SW = t.SW; c.np = t.np; c.nseg = t.nseg; c.rows_max = t.rows_max;
+    c.CW = t.CW; c.SW = t.SW; c.np = t.np; c.nseg = t.nseg; c.rows_max = t.rows_max; c.psum_accum = t.accum;
     c.evict_first = ((double)h->nrows * (double)h->n * 8.0 > 96.0 * 1024 * 1024) ? 1 : 0;
-    if (const char* e = getenv("CCQP_EVICT_FIRST")) c.evict_first = atoi(e);
+    c.evict_first = env_int("CCQP_EVICT_FIRST", c.evict_first, ok_bool);
 }
+
+constexpr int op_slot(int op) { return op < 100 ? op : 7 + (op - 100); }
 
 template <int OP>
 ccqp_status launch_dense(ccqp_handle* h, DenseCtx& c, const Tiling& t, bool cooperative) {
-    static size_t configured = 0;
-    if (t.smem > configured) {
-        CU(h, cudaFuncSetAttribute(dense_kernel<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
-        configured = 220 * 1024;
+    if (t.smem > kDenseSmemLimit) {
+        h->last_error = "dense tiling needs more shared memory than one SM has";
+        return CCQP_ERR_UNSUPPORTED;
+    }
+    if (!(h->smem_attr_mask & (1u << op_slot(OP)))) {
+        CU(h, cudaFuncSetAttribute(dense_kernel<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDenseSmemLimit));
+        h->smem_attr_mask |= 1u << op_slot(OP);
     }
     if (cooperative) CU(h, cudaMemsetAsync(h->flags.p, 0, kSyncBytes, h->stream));   // barrier counters
     void* args[] = {&c};
@@ -432,6 +480,10 @@ ccqp_status ccqp_solve_async(ccqp_handle* h, int solver, const ccqp_params* para
     const bool sharded = h->world > 1;
     if (!sharded && (h->row0 != 0 || h->nrows != h->n)) return CCQP_ERR_UNSUPPORTED;   // a shard needs ccqp_comm_attach
     if (sharded && !h->comm_ready) return CCQP_ERR_NOT_READY;
+    // the exchange buffer (work vectors, {data, epoch} packet slots) must have been cleared by ccqp_comm_prepare() and
+    // a host barrier since the previous solve: packet epochs restart at 1 with every launch, so stale packets would match
+    if (sharded && !h->comm_prepared) { h->last_error = "ccqp_comm_prepare() must be called (and the ranks synchronised) before every sharded solve"; return CCQP_ERR_NOT_READY; }
+    h->comm_prepared = false;
     CU(h, cudaSetDevice(h->device));
     ccqp_status st = ensure_work(h);
     if (st != CCQP_OK) return st;
@@ -553,7 +605,7 @@ static ccqp_status run_hook(ccqp_handle* h, int op, const double* in, double* ou
     if ((st = copy_in(h, w + W_HIN * npad, in, n_in, memtype)) != CCQP_OK) return st;
     Tiling t;
     if (h->have_matrix()) t = choose_tiling(h);
-    else { t.grid = (int)std::max<long long>(1, std::min<long long>(h->sm_count, h->n)); t.CW = 128; t.SW = 128; t.np = 1; t.nseg = 1; t.rows_max = 1; t.smem = dense_smem_bytes(128, 1, 1); }
+    else { t.grid = (int)std::max<long long>(1, std::min<long long>(h->sm_count, h->n)); t.CW = 128; t.SW = 128; t.np = 1; t.nseg = 1; t.rows_max = 1; t.accum = 0; t.smem = dense_smem_bytes(128, 1, 1); }
     DenseCtx c;
     fill_ctx(h, c, t);
     if (op == OP_GEMV) st = launch_dense<OP_GEMV>(h, c, t, false);
@@ -637,6 +689,51 @@ ccqp_status ccqp_debug_divide(ccqp_handle* h, const double* a0, const double* a1
     return CCQP_OK;
 }
 
+ccqp_status ccqp_fp64_peak(ccqp_handle* h, int blocks_per_sm, int threads_per_block, double* tflops) {
+    if (!h || !tflops || blocks_per_sm < 1 || blocks_per_sm > 32 || threads_per_block < 32 || threads_per_block > 256 ||
+        threads_per_block % 32 != 0)
+        return CCQP_ERR_INVALID_ARG;
+    CU(h, cudaSetDevice(h->device));
+    CU(h, h->out_dev.ensure(4096));
+    const int grid = h->sm_count * blocks_per_sm;
+    int iters = 1 << 12;
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {          // rep 0 is the warm-up; the best of the rest counts
+        CU(h, cudaEventRecord(h->ev0, h->stream));
+        fp64_peak_kernel<<<grid, threads_per_block, 0, h->stream>>>(h->out_dev.as<double>(), iters, 0.999999, 1e-7);
+        CU(h, cudaGetLastError());
+        CU(h, cudaEventRecord(h->ev1, h->stream));
+        CU(h, cudaStreamSynchronize(h->stream));
+        float ms = 0.f;
+        CU(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+        h->launches += 1;
+        const double flops = 2.0 * kPeakFmaPerIter * (double)iters * (double)grid * threads_per_block;
+        if (rep == 0) { if (ms < 20.f) iters = (int)std::min(1.0e6, iters * 20.0 / std::max(ms, 0.05f)); continue; }
+        best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    *tflops = best;
+    return CCQP_OK;
+}
+
+ccqp_status ccqp_microbench(ccqp_handle* h, double* cycles_per_op, int32_t n_out) {
+    if (!h || !cycles_per_op || n_out < PROBE_COUNT) return CCQP_ERR_INVALID_ARG;
+    CU(h, cudaSetDevice(h->device));
+    CU(h, h->out_dev.ensure(4096));
+    long long* dcyc = reinterpret_cast<long long*>(h->out_dev.as<char>() + 1024);
+    double* sink = reinterpret_cast<double*>(h->out_dev.as<char>() + 2048);
+    const int reps = 2048;
+    long long cyc[PROBE_COUNT];
+    for (int rep = 0; rep < 2; ++rep) {
+        probe_kernel<<<1, 64, 0, h->stream>>>(dcyc, sink, reps, 0.75, 0.999999);
+        CU(h, cudaGetLastError());
+        CU(h, cudaMemcpyAsync(cyc, dcyc, sizeof(cyc), cudaMemcpyDeviceToHost, h->stream));
+        CU(h, cudaStreamSynchronize(h->stream));
+        h->launches += 1;
+    }
+    for (int k = 0; k < PROBE_COUNT; ++k) cycles_per_op[k] = (double)cyc[k] / reps;
+    return CCQP_OK;
+}
+
 struct CommDesc {                 // CCQP_COMM_DESC_BYTES = 128
     cudaIpcMemHandle_t handle;    // 64 bytes
     unsigned long long bytes;
@@ -689,6 +786,7 @@ ccqp_status ccqp_comm_prepare(ccqp_handle* h) {
     CU(h, cudaSetDevice(h->device));
     CU(h, cudaMemsetAsync(h->work.p, 0, work_bytes(h->npad), h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
+    h->comm_prepared = true;
     return CCQP_OK;
 }
 
@@ -699,7 +797,7 @@ ccqp_status ccqp_comm_detach(ccqp_handle* h) {
     for (int s = 0; s < h->world; ++s)
         if (s != h->rank && h->peer_base[s]) cudaIpcCloseMemHandle(h->peer_base[s]);
     for (int s = 0; s < kMaxWorld; ++s) h->peer_base[s] = nullptr;
-    h->world = 1; h->rank = 0; h->comm_ready = false;
+    h->world = 1; h->rank = 0; h->comm_ready = false; h->comm_prepared = false;
     return CCQP_OK;
 }
 

@@ -84,6 +84,7 @@ struct DenseCtx {
     int nseg;           // total segments per row
     int rows_max;       // max rows owned by one CTA
     int evict_first;    // stream A with L2 evict-first
+    int psum_accum;     // nseg counts the segments of ONE panel; the panels' partial sums are added up in panel order
     // test hooks
     const double* hook_in;
     double* hook_out;
@@ -100,6 +101,9 @@ struct DenseSmem {
     uint64_t* mbar;         // 2
     unsigned long long* ascratch;   // 32
 };
+
+constexpr size_t kDenseSmemLimit = 220 * 1024;    // cudaFuncAttributeMaxDynamicSharedMemorySize of the dense kernels
+constexpr size_t kDenseSmemTarget = 200 * 1024;   // what the tiling aims to stay under
 
 __host__ __device__ inline size_t dense_smem_bytes(int CW, int rows_max, int nseg) {
     size_t s = 0;
@@ -318,7 +322,10 @@ __device__ __forceinline__ void gemv_phase(Kst& k, const DenseCtx& c, const doub
                                                : dot_seg_aligned<false>(arow, vb + col0, ncol, lane);
             else acc = dot_seg_generic(arow, vb + col0, ncol, lane);
             acc = warp_sum(acc);
-            if (lane == 0) k.sm.psum[(size_t)row * nseg + p * spp_full + seg] = acc;
+            if (lane == 0) {
+                if (!c.psum_accum) k.sm.psum[(size_t)row * nseg + p * spp_full + seg] = acc;
+                else { double* q = k.sm.psum + (size_t)row * nseg + seg; *q = (p == 0) ? acc : *q + acc; }   // (row, seg) tasks of
+            }                                                           // different panels are separated by the barrier below
         }
         __syncthreads();   // every warp is done with vbuf[buf]; psum of this panel is visible
         if (tid == 0 && p + 2 < np) { fence_proxy_async(); issue(p + 2, buf); }

@@ -59,7 +59,7 @@ def batch_range(batch, rank, world):
     return i0, i0 + base + (1 if rank < extra else 0)
 
 
-def solve_batched_sharded(solver, A, b, lower_bound, upper_bound, x0=None, seeds=None, uniforms=None, n_uniforms=256,
+def solve_batched_sharded(solver, A, b, lower_bound, upper_bound, x0=None, seeds=None, uniforms=None, n_uniforms=None,
                           gather=True, group=None):
     """Batched mode on several GPUs: the problems are independent, so every rank solves its contiguous
     share on its own GPU and there is NO communication on the data path.

@@ -228,7 +228,16 @@ class CCQPSolverBase(ABC):
         self._solution_time = time.time() - time_start
         return self
 
-    def solve_batched(self, A, b, lower_bound, upper_bound, x0=None, seeds=None, uniforms=None, n_uniforms=256,
+    def _batched_draws(self, batch):
+        """Length of the per-problem U[0,1) stream for batched SPG when the caller gives none: one sample per
+        iteration is consumed, iterations <= max_mv, so max_mv samples can never run out; capped so the
+        host-drawn streams of the whole batch stay below 1 GiB (a problem that does run out is reported,
+        never returned as converged)."""
+        mx = self.max_matrix_vector_multiplications
+        cap = max(256, (1 << 30) // (8 * max(int(batch), 1)))
+        return max(1, int(min(mx, cap))) if np.isfinite(mx) else min(cap, 4096)
+
+    def solve_batched(self, A, b, lower_bound, upper_bound, x0=None, seeds=None, uniforms=None, n_uniforms=None,
                       device=-1):
         """Extension: solve `batch` independent box-constrained QPs in one persistent kernel.
 
@@ -236,7 +245,10 @@ class CCQPSolverBase(ABC):
         device).  Problem i equals `type(self)(tol, max_mv).solve(A[i], b[i], x0[i],
         BoxProjOp(n, lb[i], ub[i]))` of the reference run after `np.random.seed(seeds[i])`.
         For SPG pass either `seeds` (the streams are drawn on the host with RandomState(seed))
-        or `uniforms` [batch, K].  Results are per-problem arrays on the `solution*` properties."""
+        or `uniforms` [batch, K].  Results are per-problem arrays on the `solution*` properties;
+        `solution_status` holds the per-problem ccqp_status raised inside the kernel.  A problem whose
+        SPG step bound is NaN raises OverflowError (np.random.uniform does, solvers.py:959); a problem
+        that used up its uniform stream raises CCQPError naming the problems (pass more samples)."""
         time_start = time.time()
         if not self.quiet:
             print("solving " + self._label)
@@ -256,6 +268,8 @@ class CCQPSolverBase(ABC):
             if uniforms is None:
                 if seeds is None:
                     seeds = np.arange(batch)
+                if n_uniforms is None:
+                    n_uniforms = self._batched_draws(batch)
                 uniforms = np.empty((batch, n_uniforms))
                 for i, s in enumerate(seeds):
                     uniforms[i] = np.random.RandomState(int(s)).random_sample(n_uniforms)
@@ -293,6 +307,15 @@ class CCQPSolverBase(ABC):
         self._launches = int(summary.kernel_launches)
         self._uniforms_used = rec["draws"].copy()
         self._solution_time = time.time() - time_start
+        bad = np.flatnonzero(self._batched_status != _capi.OK)
+        if bad.size:
+            first = int(self._batched_status[bad[0]])
+            which = ", ".join(str(int(i)) for i in bad[:8]) + (" ..." if bad.size > 8 else "")
+            if first == _capi.ERR_RANGE:
+                raise OverflowError("Range exceeds valid bounds (problems %s)" % which)     # np.random.uniform(lo, nan)
+            raise _capi.CCQPError(first, "%s in %d of %d problems (%s); their results are marked not converged%s" % (
+                _capi.load().ccqp_status_string(first).decode(), bad.size, batch, which,
+                "; pass a longer `uniforms` stream / larger n_uniforms (used K = %d)" % K if first == _capi.ERR_UNIFORMS_EXHAUSTED else ""))
         return self
 
     # -- result properties, solvers.py:172-194 ---------------------------------------------------
@@ -339,6 +362,11 @@ class CCQPSolverBase(ABC):
     @property
     def solution_kernel_launches(self):
         return self._launches
+
+    @property
+    def solution_status(self):
+        """Batched solves: per-problem ccqp_status raised inside the kernel (0 = none)."""
+        return getattr(self, "_batched_status", None)
 
 
 class CCQPSolverPGD(CCQPSolverBase):

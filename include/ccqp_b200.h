@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define CCQP_ABI_VERSION 2
+#define CCQP_ABI_VERSION 3
 
 typedef enum ccqp_status {
     CCQP_OK = 0,
@@ -41,7 +41,10 @@ typedef enum ccqp_status {
     CCQP_ERR_UNIFORMS_EXHAUSTED = 7,     /* SPG consumed every supplied uniform sample              */
     CCQP_ERR_RANGE = 8,                  /* SPG step bound is NaN: np.random.uniform raises
                                             OverflowError there (solvers.py:959)                    */
-    CCQP_ERR_DEVICE_TIMEOUT = 9,         /* an in-kernel barrier timed out (kernel aborted)         */
+    CCQP_ERR_DEVICE_TIMEOUT = 9,         /* an in-kernel barrier timed out (~4 s): the kernel trapped.
+                                            A trap is a sticky CUDA error: the process's CUDA context
+                                            is gone, this handle AND every other handle / CUDA user of
+                                            the process are dead; the process has to be restarted      */
     CCQP_ERR_COMM = 10                   /* multi-GPU exchange setup failed                         */
 } ccqp_status;
 
@@ -194,6 +197,19 @@ ccqp_status ccqp_normal(ccqp_handle* h, const double* x, double* out, int memtyp
  * for its three divisions by d.Ad (solvers.py:954,955,966); must equal IEEE division bit for bit. DEVICE pointers. */
 ccqp_status ccqp_debug_divide(ccqp_handle* h, const double* a0, const double* a1, const double* a2, const double* b,
                             double* q0, double* q1, double* q2, int64_t count);
+
+/* ---- measurement hooks (roofline denominators; nothing here is on the solve path) -------------
+ * Measured FP64 throughput of the handle's device in TFLOP/s (2 flops per DFMA): every thread of
+ * blocks_per_sm x threads_per_block resident threads per SM runs 8 independent DFMA chains.  With
+ * the SM full (8 x 256) this is the fp64 term of the batched mode's roofline,
+ * max(HBM bytes / BW, 2 n^2 * mat-vecs / FP64 peak); with 6 x 64 it is what
+ * the batched kernel's own occupancy could issue if it executed nothing but its mat-vec DFMAs. */
+ccqp_status ccqp_fp64_peak(ccqp_handle* h, int blocks_per_sm, int threads_per_block, double* tflops);
+/* SM cycles per dependent operation, one warp, in the order DFMA, DADD, DMUL, SHFL.64+DADD, IEEE
+ * division+DADD, sqrt+DADD, LDS.128 (all lanes one address)+DADD, LDS.128 (distinct)+DADD,
+ * STS+bar+LDS+DADD+bar, bar.sync (64 threads), DSETP+select+DADD.  n_out >= 11.  Feeds the cycle
+ * model of the batched kernel in DESIGN.md. */
+ccqp_status ccqp_microbench(ccqp_handle* h, double* cycles_per_op, int32_t n_out);
 
 /* ---- multi-GPU (row-sharded dense solves, one process per GPU) --------------------------------
  * Nothing in the reference corresponds to this (it is single-process NumPy).  A is row-sharded:

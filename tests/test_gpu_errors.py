@@ -100,3 +100,67 @@ def test_infinite_bounds_mean_no_bound():
     ref = make_solver(pr.BBPGD, 1e-8, 500)
     ref.solve(A, b, convex_proj_op=ss.DisjointProjOp(ss.UpperBoundProjOp(10, hi[:10]), ss.IdentityProjOp(n - 10)))
     assert s.solution_converged and np.array_equal(np.asarray(s.solution), np.asarray(ref.solution))
+
+
+def test_batched_problem_that_runs_out_of_uniforms_is_reported_not_converged():
+    """a batched SPG problem that used up its uniform stream must not come back as converged."""
+    batch, n = 6, 32
+    A = np.empty((batch, n, n)); b = np.empty((batch, n))
+    for i in range(batch):
+        A[i], b[i] = pr.shift_problem(n, 40 + i, 0.05)
+    lb, ub = -np.ones((batch, n)), np.ones((batch, n))
+    s = make_solver(pr.SPG, 1e-12, 5000)
+    with pytest.raises(_capi.CCQPError) as e:
+        s.solve_batched(A, b, lb, ub, seeds=np.arange(batch), n_uniforms=3)
+    assert e.value.status == _capi.ERR_UNIFORMS_EXHAUSTED
+    st = s.solution_status
+    assert np.any(st == _capi.ERR_UNIFORMS_EXHAUSTED)
+    assert not np.any(np.asarray(s.solution_converged)[st != 0])          # status != 0  =>  not converged
+    # the default stream length (max_mv samples) cannot run out
+    s2 = make_solver(pr.SPG, 1e-8, 400)
+    s2.solve_batched(A, b, lb, ub, seeds=np.arange(batch))
+    assert np.all(s2.solution_status == 0)
+    bn = b.copy()
+    bn[2, 0] = np.nan
+    with pytest.raises(OverflowError):                                    # np.random.uniform(lo, nan), solvers.py:959
+        make_solver(pr.SPG, 1e-8, 400).solve_batched(A, bn, lb, ub, seeds=np.arange(batch))
+
+
+def test_sharded_solve_without_prepare_is_refused():
+    """the C-ABI refuses a sharded solve whose exchange buffer was not cleared by ccqp_comm_prepare()."""
+    h = _capi.Handle()
+    lib = h.lib
+    n = 64
+    A, b = pr.shift_problem(n, 0)
+    desc = (ctypes.c_ubyte * 128)()
+    assert lib.ccqp_comm_export(h.h, 0, 2, n, desc) == 0
+    assert lib.ccqp_comm_prepare(h.h) == 5                                # not attached yet
+    h.close()
+
+
+def test_two_devices_from_one_process():
+    """kernel attributes are per device.  One process solves n = 4096 (> 48 KB of dynamic shared
+    memory) on device 0, then on device 1, then through a SolvePipeline bound to device 1."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    from ccqppy_b200.pipeline import SolvePipeline
+    n = 4096
+    A, b = pr.shift_problem(n, 3)
+    op = ss.BoxProjOp(n)
+    sols = []
+    for dev in (0, 1):
+        s = make_solver(pr.BBPGD, 1e-7, 500)
+        s.solve(A, b, convex_proj_op=op, device=dev)
+        assert s.solution_converged
+        sols.append(np.asarray(s.solution).copy())
+        Ad = torch.from_numpy(A).to("cuda:%d" % dev)
+        s.solve(Ad, torch.from_numpy(b).to(Ad.device), convex_proj_op=op)
+        assert np.array_equal(s.solution.cpu().numpy(), sols[-1])
+    assert np.array_equal(sols[0], sols[1])
+    pipe = SolvePipeline(make_solver(pr.BBPGD, 1e-7, 500), depth=2, device=1)
+    for _ in range(3):
+        pipe.submit(torch.from_numpy(A).pin_memory(), torch.from_numpy(b).pin_memory(), convex_proj_op=op)
+    res = pipe.results()
+    pipe.close()
+    assert len(res) == 3 and all(np.array_equal(np.asarray(r.solution), sols[0]) for r in res)
