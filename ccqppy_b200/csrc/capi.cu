@@ -13,8 +13,8 @@
 #include <string>
 #include <vector>
 
-#include "batched.cuh"
 #include "dense.cuh"
+#include "internal.h"
 #include "microbench.cuh"
 
 using namespace ccqp;
@@ -71,6 +71,8 @@ struct ccqp_handle {
     char* peer_base[kMaxWorld] = {nullptr};
     bool comm_ready = false;
     bool comm_prepared = false;     // ccqp_comm_prepare() ran since the last sharded solve (stale packets would match)
+    bool emulated = false;          // rank of an emulated box (ccqp_debug_emulate_ranks): peers live on the same device
+    DevBuf emu_ctx;                 // rank 0 of an emulated box: the ranks' kernel contexts
     // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute of each kernel instantiation: one bit per
     // instantiation, kept per handle (a handle owns exactly one device)
     unsigned smem_attr_mask = 0;
@@ -324,10 +326,10 @@ ccqp_status ccqp_destroy(ccqp_handle* h) {
     if (!h) return CCQP_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    if (h->world > 1) ccqp_comm_detach(h);
+    if (h->world > 1 && !h->emulated) ccqp_comm_detach(h);
     DevBuf* bufs[] = {&h->a_own, &h->lo, &h->hi, &h->ekind, &h->bkind, &h->boff, &h->bdim, &h->bpar, &h->small_ids,
                       &h->big_ids, &h->work, &h->partials, &h->flags, &h->out_dev, &h->uniforms,
-                      &h->batched_ws, &h->dbg, &h->ptr_own, &h->idx_own, &h->val_own};
+                      &h->batched_ws, &h->dbg, &h->ptr_own, &h->idx_own, &h->val_own, &h->emu_ctx};
     for (DevBuf* b : bufs) b->release();
     if (h->out_host) cudaFreeHost(h->out_host);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -470,46 +472,82 @@ ccqp_status ccqp_set_projection(ccqp_handle* h, const ccqp_block* blocks, int64_
     return CCQP_OK;
 }
 
-ccqp_status ccqp_solve_async(ccqp_handle* h, int solver, const ccqp_params* params, const double* b, const double* x0,
-                             const double* uniforms, int64_t n_uniforms, double* x_out, int memtype) {
-    if (!h || !b || !x_out || !params_ok(params, solver) || solver < 0 || solver > CCQP_SOLVER_MPRGP)
-        return CCQP_ERR_INVALID_ARG;
+}  // extern "C"
+
+namespace {
+// Everything of a dense solve up to (not including) the kernel launch: argument checks, work buffers, input
+// copies on `stream`, the kernel context.  Shared by ccqp_solve_async() and ccqp_debug_solve_emulated().
+ccqp_status prepare_dense_solve(ccqp_handle* h, cudaStream_t stream, int solver, const ccqp_params* params, const double* b,
+                                const double* x0, const double* uniforms, int64_t n_uniforms, int memtype, bool zero_work,
+                                DenseCtx& c, Tiling& t) {
+    if (!h || !b || !params_ok(params, solver) || solver < 0 || solver > CCQP_SOLVER_MPRGP) return CCQP_ERR_INVALID_ARG;
     if (h->pending) return CCQP_ERR_NOT_READY;          // one solve in flight per handle
     if (!h->have_matrix() || !h->have_proj) return CCQP_ERR_NOT_READY;
     if (h->proj_n != h->n) return CCQP_ERR_INVALID_ARG;
-    const bool sharded = h->world > 1;
-    if (!sharded && (h->row0 != 0 || h->nrows != h->n)) return CCQP_ERR_UNSUPPORTED;   // a shard needs ccqp_comm_attach
-    if (sharded && !h->comm_ready) return CCQP_ERR_NOT_READY;
-    // the exchange buffer (work vectors, {data, epoch} packet slots) must have been cleared by ccqp_comm_prepare() and
-    // a host barrier since the previous solve: packet epochs restart at 1 with every launch, so stale packets would match
-    if (sharded && !h->comm_prepared) { h->last_error = "ccqp_comm_prepare() must be called (and the ranks synchronised) before every sharded solve"; return CCQP_ERR_NOT_READY; }
-    h->comm_prepared = false;
+    if (solver == CCQP_SOLVER_SPG && (n_uniforms < 0 || (n_uniforms > 0 && !uniforms))) return CCQP_ERR_INVALID_ARG;
     CU(h, cudaSetDevice(h->device));
     ccqp_status st = ensure_work(h);
     if (st != CCQP_OK) return st;
     const long long n = h->n, npad = h->npad;
     double* w = reinterpret_cast<double*>(h->work.as<char>() + kSymVecOff);
-    // zero everything (vector tails must be zero), then fill.  Sharded: ccqp_comm_prepare() did it
+    // zero everything (vector tails must be zero), then fill.  Real sharded solves: ccqp_comm_prepare() did it
     // before the host-side barrier, because peers write into this buffer as soon as they start.
-    if (!sharded) CU(h, cudaMemsetAsync(h->work.p, 0, work_bytes(npad), h->stream));
-    else if (!x0) CU(h, cudaMemsetAsync(w + W_X0 * npad, 0, (size_t)npad * 8, h->stream));
-    if ((st = copy_in(h, w + W_B * npad, b, n, memtype)) != CCQP_OK) return st;
-    if (x0 && (st = copy_in(h, w + W_X0 * npad, x0, n, memtype)) != CCQP_OK) return st;
-    const Tiling t = choose_tiling(h);
-    DenseCtx c;
+    if (zero_work) CU(h, cudaMemsetAsync(h->work.p, 0, work_bytes(npad), stream));
+    else if (!x0) CU(h, cudaMemsetAsync(w + W_X0 * npad, 0, (size_t)npad * 8, stream));
+    const cudaMemcpyKind kind = memtype == CCQP_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    CU(h, cudaMemcpyAsync(w + W_B * npad, b, (size_t)n * 8, kind, stream));
+    if (x0) CU(h, cudaMemcpyAsync(w + W_X0 * npad, x0, (size_t)n * 8, kind, stream));
+    t = choose_tiling(h);
     fill_ctx(h, c, t);
     c.tol = params->tol; c.max_mv = params->max_mv; c.step = params->step_size;
     c.tau = params->tau; c.sig1 = params->sigma1; c.sig2 = params->sigma2; c.m = params->m;
     if (solver == CCQP_SOLVER_SPG) {
-        if (n_uniforms < 0 || (n_uniforms > 0 && !uniforms)) return CCQP_ERR_INVALID_ARG;
         if (memtype == CCQP_MEM_DEVICE) c.uniforms = uniforms;
         else {
             CU(h, h->uniforms.ensure((size_t)std::max<int64_t>(n_uniforms, 1) * 8));
-            if (n_uniforms) CU(h, cudaMemcpyAsync(h->uniforms.p, uniforms, (size_t)n_uniforms * 8, cudaMemcpyHostToDevice, h->stream));
+            if (n_uniforms) CU(h, cudaMemcpyAsync(h->uniforms.p, uniforms, (size_t)n_uniforms * 8, cudaMemcpyHostToDevice, stream));
             c.uniforms = h->uniforms.as<double>();
         }
         c.n_uniforms = n_uniforms;
     }
+    return CCQP_OK;
+}
+
+void fill_result(const ccqp_handle* h, const DenseOut* o, float ms, long long launches, ccqp_result* result) {
+    const long long n = h->n;
+    std::memset(result, 0, sizeof(*result));
+    result->residual = o->residual;
+    result->gpu_seconds = ms * 1e-3;
+    result->mv_count = o->mv;
+    result->gemv_count = o->gemv;
+    result->iterations = o->iters;
+    result->uniforms_used = o->draws;
+    result->converged = o->converged;
+    result->status = o->status;
+    result->hbm_bytes = h->d_val ? (double)o->gemv * (12.0 * (double)h->nnz + 8.0 * (double)(h->nrows + 1) + 8.0 * (double)n + 8.0 * (double)h->nrows)
+                                 : (double)o->gemv * (8.0 * (double)h->nrows * (double)n + 8.0 * (double)n + 8.0 * (double)h->nrows);
+    result->kernel_launches = launches;
+}
+}  // namespace
+
+extern "C" {
+
+ccqp_status ccqp_solve_async(ccqp_handle* h, int solver, const ccqp_params* params, const double* b, const double* x0,
+                             const double* uniforms, int64_t n_uniforms, double* x_out, int memtype) {
+    if (!h || !x_out) return CCQP_ERR_INVALID_ARG;
+    h->last_error.clear();
+    if (h->emulated) { h->last_error = "handles of an emulated box solve through ccqp_debug_solve_emulated()"; return CCQP_ERR_UNSUPPORTED; }
+    const bool sharded = h->world > 1;
+    if (!sharded && h->have_matrix() && (h->row0 != 0 || h->nrows != h->n)) return CCQP_ERR_UNSUPPORTED;   // a shard needs ccqp_comm_attach
+    if (sharded && !h->comm_ready) return CCQP_ERR_NOT_READY;
+    // the exchange buffer (work vectors, {data, epoch} packet slots) must have been cleared by ccqp_comm_prepare() and
+    // a host barrier since the previous solve: packet epochs restart at 1 with every launch, so stale packets would match
+    if (sharded && !h->comm_prepared) { h->last_error = "ccqp_comm_prepare() must be called (and the ranks synchronised) before every sharded solve"; return CCQP_ERR_NOT_READY; }
+    DenseCtx c;
+    Tiling t;
+    ccqp_status st = prepare_dense_solve(h, h->stream, solver, params, b, x0, uniforms, n_uniforms, memtype, !sharded, c, t);
+    if (st != CCQP_OK) return st;
+    h->comm_prepared = false;
     const bool dbg_timing = getenv("CCQP_DEBUG_TIMING") != nullptr;
     if (dbg_timing) {
         CU(h, h->dbg.ensure(kDbgSlots * kDbgIters * 8));
@@ -521,7 +559,7 @@ ccqp_status ccqp_solve_async(ccqp_handle* h, int solver, const ccqp_params* para
     if ((st = launch_by_solver(h, solver, c, t)) != CCQP_OK) return st;
     CU(h, cudaEventRecord(h->ev1, h->stream));
     CU(h, cudaMemcpyAsync(h->out_host, h->out_dev.p, sizeof(DenseOut), cudaMemcpyDeviceToHost, h->stream));
-    if ((st = copy_out(h, x_out, c.x_out, n, memtype)) != CCQP_OK) return st;
+    if ((st = copy_out(h, x_out, c.x_out, h->n, memtype)) != CCQP_OK) return st;
     h->pending = true; h->pending_solver = solver; h->pending_launches0 = launches0; h->pending_dbg = dbg_timing;
     return CCQP_OK;
 }
@@ -532,7 +570,7 @@ ccqp_status ccqp_solve_wait(ccqp_handle* h, ccqp_result* result) {
     h->pending = false;
     CU(h, cudaSetDevice(h->device));
     const int solver = h->pending_solver;
-    const long long launches0 = h->pending_launches0, n = h->n;
+    const long long launches0 = h->pending_launches0;
     const bool dbg_timing = h->pending_dbg;
     cudaError_t e = cudaStreamSynchronize(h->stream);
     if (e != cudaSuccess) {
@@ -563,18 +601,7 @@ ccqp_status ccqp_solve_wait(ccqp_handle* h, ccqp_result* result) {
         }
     }
     const DenseOut* o = reinterpret_cast<const DenseOut*>(h->out_host);
-    std::memset(result, 0, sizeof(*result));
-    result->residual = o->residual;
-    result->gpu_seconds = ms * 1e-3;
-    result->mv_count = o->mv;
-    result->gemv_count = o->gemv;
-    result->iterations = o->iters;
-    result->uniforms_used = o->draws;
-    result->converged = o->converged;
-    result->status = o->status;
-    result->hbm_bytes = h->d_val ? (double)o->gemv * (12.0 * (double)h->nnz + 8.0 * (double)(h->nrows + 1) + 8.0 * (double)n + 8.0 * (double)h->nrows)
-                                 : (double)o->gemv * (8.0 * (double)h->nrows * (double)n + 8.0 * (double)n + 8.0 * (double)h->nrows);
-    result->kernel_launches = h->launches - launches0;
+    fill_result(h, o, ms, h->launches - launches0, result);
     return (ccqp_status)o->status;
 }
 
@@ -661,7 +688,7 @@ ccqp_status ccqp_solve_batched(ccqp_handle* h, int solver, const ccqp_params* pa
     CU(h, cudaSetDevice(h->device));
     std::string err;
     int launches = 0;
-    ccqp_status st = (ccqp_status)batched_solve(h->stream, h->sm_count, h->batched_ws.p, h->batched_ws.cap, solver, *params,
+    ccqp_status st = (ccqp_status)batched_solve_entry(h->stream, h->sm_count, solver, *params,
                                                 batch, n, A, b, x0, lb, ub, uniforms, n_uniforms, x_out, memtype, results,
                                                 summary, h->ev0, h->ev1, &launches, err,
                                                 [&](size_t bytes) -> void* { return h->batched_ws.ensure(bytes) == cudaSuccess ? h->batched_ws.p : nullptr; });
@@ -732,6 +759,76 @@ ccqp_status ccqp_microbench(ccqp_handle* h, double* cycles_per_op, int32_t n_out
     }
     for (int k = 0; k < PROBE_COUNT; ++k) cycles_per_op[k] = (double)cyc[k] / reps;
     return CCQP_OK;
+}
+
+ccqp_status ccqp_debug_emulate_ranks(ccqp_handle* const* hs, int world, int64_t n) {
+    if (!hs || world < 2 || world > kMaxWorld || n <= 0) return CCQP_ERR_INVALID_ARG;
+    for (int r = 0; r < world; ++r)
+        if (!hs[r] || hs[r]->device != hs[0]->device || (hs[r]->world > 1 && !hs[r]->emulated)) return CCQP_ERR_INVALID_ARG;
+    ccqp_handle* h0 = hs[0];
+    CU(h0, cudaSetDevice(h0->device));
+    cudaDeviceProp prop;
+    CU(h0, cudaGetDeviceProperties(&prop, h0->device));
+    if (prop.multiProcessorCount / world < 1) return CCQP_ERR_UNSUPPORTED;
+    const long long npad = round_up(n, 64) + 64;
+    for (int r = 0; r < world; ++r) {
+        ccqp_handle* h = hs[r];
+        CU(h, cudaStreamSynchronize(h->stream));
+        h->work.release();
+        CU(h, h->work.ensure(work_bytes(npad)));
+        h->npad = npad; h->n = n;
+        h->world = world; h->rank = r; h->emulated = true; h->comm_ready = true; h->comm_prepared = false;
+        h->sm_count = prop.multiProcessorCount / world;     // all ranks' CTAs must be co-resident in ONE cooperative launch
+    }
+    for (int r = 0; r < world; ++r)
+        for (int s = 0; s < kMaxWorld; ++s) hs[r]->peer_base[s] = s < world ? hs[s]->work.as<char>() : nullptr;
+    return CCQP_OK;
+}
+
+ccqp_status ccqp_debug_solve_emulated(ccqp_handle* const* hs, int world, int solver, const ccqp_params* params, const double* b,
+                                      const double* x0, const double* uniforms, int64_t n_uniforms, double* x_out, int memtype,
+                                      ccqp_result* results) {
+    if (!hs || !x_out || !results || world < 2 || world > kMaxWorld) return CCQP_ERR_INVALID_ARG;
+    for (int r = 0; r < world; ++r)
+        if (!hs[r] || !hs[r]->emulated || hs[r]->world != world || hs[r]->rank != r) return CCQP_ERR_INVALID_ARG;
+    ccqp_handle* h0 = hs[0];
+    h0->last_error.clear();
+    cudaStream_t stream = h0->stream;
+    std::vector<DenseCtx> ctxs((size_t)world);
+    size_t smem = 0;
+    int G = 0;
+    for (int r = 0; r < world; ++r) {
+        CU(hs[r], cudaStreamSynchronize(hs[r]->stream));          // set_matrix / set_projection copies of this rank
+        Tiling t;
+        const ccqp_status st = prepare_dense_solve(hs[r], stream, solver, params, b, x0, uniforms, n_uniforms, memtype, true, ctxs[r], t);
+        if (st != CCQP_OK) { h0->last_error = hs[r]->last_error; return st; }
+        if (r > 0 && t.grid != G) { h0->last_error = "ranks disagree on the grid"; return CCQP_ERR_COMM; }
+        G = t.grid;
+        smem = std::max(smem, t.smem);
+        CU(hs[r], cudaMemsetAsync(hs[r]->flags.p, 0, kSyncBytes, stream));
+    }
+    if (smem > kDenseSmemLimit) return CCQP_ERR_UNSUPPORTED;
+    CU(h0, h0->emu_ctx.ensure(sizeof(DenseCtx) * world));
+    CU(h0, cudaMemcpyAsync(h0->emu_ctx.p, ctxs.data(), sizeof(DenseCtx) * world, cudaMemcpyHostToDevice, stream));
+    CU(h0, cudaEventRecord(h0->ev0, stream));
+    CU(h0, launch_dense_emu(solver, h0->emu_ctx.as<DenseCtx>(), world, G, smem, stream));
+    CU(h0, cudaEventRecord(h0->ev1, stream));
+    h0->launches += 1;
+    std::vector<DenseOut> outs((size_t)world);
+    const cudaMemcpyKind kind = memtype == CCQP_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    for (int r = 0; r < world; ++r) {
+        CU(h0, cudaMemcpyAsync(&outs[r], hs[r]->out_dev.p, sizeof(DenseOut), cudaMemcpyDeviceToHost, stream));
+        CU(h0, cudaMemcpyAsync(x_out + (size_t)r * hs[r]->n, ctxs[r].x_out, (size_t)hs[r]->n * 8, kind, stream));
+    }
+    cudaError_t e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) {
+        h0->last_error = std::string("emulated solver kernel: ") + cudaGetErrorString(e);
+        return e == cudaErrorLaunchFailure ? CCQP_ERR_DEVICE_TIMEOUT : CCQP_ERR_CUDA;
+    }
+    float ms = 0.f;
+    CU(h0, cudaEventElapsedTime(&ms, h0->ev0, h0->ev1));
+    for (int r = 0; r < world; ++r) fill_result(hs[r], &outs[r], ms, 1, &results[r]);
+    return (ccqp_status)outs[0].status;
 }
 
 struct CommDesc {                 // CCQP_COMM_DESC_BYTES = 128

@@ -118,6 +118,7 @@ __host__ __device__ inline size_t dense_smem_bytes(int CW, int rows_max, int nse
 struct Kst {                // per-thread kernel state
     unsigned epoch, xepoch; // grid_xsync counts (identical in every thread of every CTA of every rank)
     DenseSmem sm;
+    int bid, nblk;          // this CTA's index in / the size of the rank's grid (blockIdx.x / gridDim.x unless ranks are emulated)
     int gtid, gstride;
     int r0, r1;             // rows of this CTA (global indices)
     unsigned par[2];        // mbarrier phase parity per buffer
@@ -133,7 +134,7 @@ struct Kst {                // per-thread kernel state
 template <bool kCross>
 __device__ __forceinline__ void barrier_only(Kst& k, const DenseCtx& c) {
     unsigned long long none[1] = {0};
-    grid_xsync<0, false>(c.gs, c.x, k.epoch, k.xepoch, kCross, none, reinterpret_cast<unsigned long long*>(k.sm.scratch));
+    grid_xsync<0, false>(c.gs, c.x, k.epoch, k.xepoch, kCross, none, reinterpret_cast<unsigned long long*>(k.sm.scratch), k.bid, k.nblk);
 }
 
 // store into a vector that a later mat-vec reads in full: the owning rank also writes the entry
@@ -159,7 +160,7 @@ __device__ __forceinline__ void reduce_sync(Kst& k, const DenseCtx& c, double (&
     unsigned long long v[K];
 #pragma unroll
     for (int j = 0; j < K; ++j) v[j] = (unsigned long long)__double_as_longlong(a[j]);
-    grid_xsync<K, false>(c.gs, c.x, k.epoch, k.xepoch, kCross, v, reinterpret_cast<unsigned long long*>(k.sm.scratch));
+    grid_xsync<K, false>(c.gs, c.x, k.epoch, k.xepoch, kCross, v, reinterpret_cast<unsigned long long*>(k.sm.scratch), k.bid, k.nblk);
 #pragma unroll
     for (int j = 0; j < K; ++j) a[j] = __longlong_as_double((long long)v[j]);
 }
@@ -172,7 +173,7 @@ __device__ __forceinline__ unsigned long long and_sync(Kst& k, const DenseCtx& c
     __syncthreads();
     unsigned long long v[1] = {~0ull};
     for (int w = 0; w < kDenseWarps; ++w) v[0] &= k.sm.ascratch[w];      // every thread: a one-CTA solve returns these as they are
-    grid_xsync<1, true>(c.gs, c.x, k.epoch, k.xepoch, false, v, reinterpret_cast<unsigned long long*>(k.sm.scratch));
+    grid_xsync<1, true>(c.gs, c.x, k.epoch, k.xepoch, false, v, reinterpret_cast<unsigned long long*>(k.sm.scratch), k.bid, k.nblk);
     return v[0];
 }
 
@@ -376,7 +377,7 @@ __device__ __forceinline__ double residual_partial(Kst& k, const DenseCtx& c, do
 
 __device__ __forceinline__ void finish(Kst& k, const DenseCtx& c, const double* xsol, double res, int status) {
     CCQP_ELEMS(i) c.x_out[i] = ld_cg(xsol + i);   // every rank holds the full solution
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (k.bid == 0 && threadIdx.x == 0) {
         DenseOut o;
         o.residual = res;
         o.mv = k.mv; o.gemv = k.gemv; o.iters = k.iters; o.draws = k.draws;
@@ -388,7 +389,7 @@ __device__ __forceinline__ void finish(Kst& k, const DenseCtx& c, const double* 
 
 constexpr int kDbgSlots = 8, kDbgIters = 64;
 __device__ __forceinline__ void dbg_stamp(const DenseCtx& c, long long it, int slot) {
-    if (c.dbg && blockIdx.x == 0 && threadIdx.x == 0 && it < kDbgIters) {
+    if (c.dbg && blockIdx.x == 0 && threadIdx.x == 0 && it < kDbgIters) {   // (the launch's first CTA = rank 0's CTA 0)
         long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         c.dbg[it * kDbgSlots + slot] = t;
@@ -485,7 +486,7 @@ __device__ void solve_pgd_family(Kst& k, const DenseCtx& c) {
 // ------------------------------------------------------------------------------------------
 // SPG-QP                                                           solvers.py:906-975
 // ------------------------------------------------------------------------------------------
-__device__ void solve_spg(Kst& k, const DenseCtx& c) {
+static __device__ void solve_spg(Kst& k, const DenseCtx& c) {
     double *x = c.vec[0], *g = c.vec[1], *d = c.vec[2];
     const double* b = c.b;
     CCQP_ELEMS(i) x[i] = c.x0[i];
@@ -681,7 +682,7 @@ __device__ void solve_apgd(Kst& k, const DenseCtx& c) {
 // Feasibility bisection (:1112-1118) in one pass: bit j of the result is set iff
 // all(isclose(yf, P(yf))) holds for yf = x - (af * 2^-j) p.  Halving is exact in fp64, so the
 // step lengths tested are bit-identical to the reference's alpha_f *= 0.5 sequence.
-__device__ unsigned long long bisect_mask(Kst& k, const DenseCtx& c, const double* x, const double* p, double af) {
+static __device__ unsigned long long bisect_mask(Kst& k, const DenseCtx& c, const double* x, const double* p, double af) {
     unsigned long long m = ~0ull;
     const ProjTable& T = c.T;
     CCQP_ELEMS(i) {
@@ -754,7 +755,7 @@ __device__ __forceinline__ void gemv_into(Kst& k, const DenseCtx& c, const doubl
     }
 }
 
-__device__ void solve_mprgp(Kst& k, const DenseCtx& c) {
+static __device__ void solve_mprgp(Kst& k, const DenseCtx& c) {
     double *xk = c.vec[0], *xn = c.vec[1], *gk = c.vec[2], *gn = c.vec[3], *p = c.vec[4], *Ap = c.vec[5];
     double *nv = c.vec[6], *w = c.vec[7], *dl = c.vec[8];
     const double* b = c.b;
@@ -925,7 +926,7 @@ __device__ void solve_mprgp(Kst& k, const DenseCtx& c) {
 // kernel
 // ------------------------------------------------------------------------------------------
 template <int OP>
-__global__ void __launch_bounds__(kDenseThreads, 1) dense_kernel(const DenseCtx c) {
+__device__ __forceinline__ void dense_body(const DenseCtx& c, const int bid, const int nblk) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Kst k;
     {
@@ -939,10 +940,12 @@ __global__ void __launch_bounds__(kDenseThreads, 1) dense_kernel(const DenseCtx 
     }
     k.epoch = 0;
     k.xepoch = 0;
-    k.gtid = blockIdx.x * kDenseThreads + threadIdx.x;
-    k.gstride = gridDim.x * kDenseThreads;
-    k.r0 = c.row0 + (int)(((long long)c.nrows * blockIdx.x) / gridDim.x);
-    k.r1 = c.row0 + (int)(((long long)c.nrows * (blockIdx.x + 1)) / gridDim.x);
+    k.bid = bid;
+    k.nblk = nblk;
+    k.gtid = bid * kDenseThreads + threadIdx.x;
+    k.gstride = nblk * kDenseThreads;
+    k.r0 = c.row0 + (int)(((long long)c.nrows * bid) / nblk);
+    k.r1 = c.row0 + (int)(((long long)c.nrows * (bid + 1)) / nblk);
     k.par[0] = k.par[1] = 0u;
     k.mv = k.gemv = k.iters = k.draws = 0;
     k.yq = 0;
@@ -966,6 +969,28 @@ __global__ void __launch_bounds__(kDenseThreads, 1) dense_kernel(const DenseCtx 
     } else if constexpr (OP == OP_NORMAL) {
         normal_pass(c.T, k.gtid, k.gstride, k.sm.scratch, [&](int i) { return c.hook_in[i]; }, c.hook_out);
     }
+}
+
+template <int OP>
+__global__ void __launch_bounds__(kDenseThreads, 1) dense_kernel(const DenseCtx c) {
+    dense_body<OP>(c, (int)blockIdx.x, (int)gridDim.x);
+}
+
+// Test vehicle for the multi-GPU exchange protocol on ONE GPU: `world` ranks inside a single cooperative launch.
+// CTAs [r*G, (r+1)*G) play rank r with rank r's context (its row shard, its work buffer, its sync words); the
+// "peer" buffers are the other ranks' buffers in the same device memory, so pub_store / grid_xsync execute exactly
+// the code of a real sharded solve (LL packets included), only the stores do not cross NVLink.  (Ranks as separate
+// launches on one GPU would deadlock: nothing guarantees that kernels that wait on one another run concurrently.)
+template <int OP>
+__global__ void __launch_bounds__(kDenseThreads, 1) dense_kernel_emu(const DenseCtx* __restrict__ ctxs, const int G) {
+    __shared__ DenseCtx c;
+    {
+        const int* src = reinterpret_cast<const int*>(ctxs + blockIdx.x / G);
+        int* dst = reinterpret_cast<int*>(&c);
+        for (int i = threadIdx.x; i < (int)(sizeof(DenseCtx) / sizeof(int)); i += kDenseThreads) dst[i] = src[i];
+    }
+    __syncthreads();
+    dense_body<OP>(c, (int)blockIdx.x % G, G);
 }
 
 }  // namespace ccqp

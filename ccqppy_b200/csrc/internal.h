@@ -1,0 +1,26 @@
+// Entry points between the translation units of libccqp_b200.so (the kernels are split over several .cu files
+// only so that they compile in parallel): capi.cu (C-ABI, dense kernels), batched.cu (batched kernels),
+// emu.cu (emulated-ranks instantiations of the dense kernels, a test vehicle).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <functional>
+#include <string>
+
+#include "../../include/ccqp_b200.h"
+
+namespace ccqp {
+
+struct DenseCtx;
+
+// batched.cu -- returns a ccqp_status; `alloc(bytes)` returns a device workspace of at least that size
+int batched_solve_entry(cudaStream_t stream, int sm_count, int solver, const ccqp_params& prm, long long batch, long long n,
+                        const double* A, const double* b, const double* x0, const double* lb, const double* ub,
+                        const double* uniforms, long long n_uniforms, double* x_out, int memtype, ccqp_result* results,
+                        ccqp_result* summary, cudaEvent_t ev0, cudaEvent_t ev1, int* launches, std::string& err,
+                        const std::function<void*(size_t)>& alloc);
+
+// emu.cu -- one cooperative launch of dense_kernel_emu<solver> over world * G CTAs
+cudaError_t launch_dense_emu(int solver, const DenseCtx* d_ctxs, int world, int G, size_t smem, cudaStream_t stream);
+
+}  // namespace ccqp

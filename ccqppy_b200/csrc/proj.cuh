@@ -128,7 +128,8 @@ __device__ __forceinline__ void project_pass(const ProjTable& T, int gtid, int g
         for (int j = 0; j < kSmallDim; ++j)
             if (j < dim) sink(off + j, t[j], R.apply(t[j], j == dim - 1));
     }
-    for (int s = blockIdx.x; s < T.nbig; s += gridDim.x) {
+    // CTA index / CTA count of this rank's grid, derived from the thread ids the caller numbers the grid with
+    for (int s = gtid / (int)blockDim.x; s < T.nbig; s += gstride / (int)blockDim.x) {
         const int b = T.big_ids[s];
         const int off = T.boff[b], dim = T.bdim[b];
         if (off < T.e0 || off >= T.e1) continue;   // CTA-uniform
@@ -212,7 +213,7 @@ __device__ void normal_pass(const ProjTable& T, int gtid, int gstride, double* s
         }
     }
     // CTA-per-leaf for large leaves
-    for (int b = blockIdx.x; b < T.nblk; b += gridDim.x) {
+    for (int b = gtid / (int)blockDim.x; b < T.nblk; b += gstride / (int)blockDim.x) {
         const int dim = T.bdim[b];
         if (dim <= kSmallDim || !owns_block(T, b)) continue;   // CTA-uniform
         const int off = T.boff[b], kind = T.bkind[b];

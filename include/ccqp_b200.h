@@ -230,6 +230,21 @@ ccqp_status ccqp_comm_attach(ccqp_handle* h, const void* all_descs /* world * CC
 ccqp_status ccqp_comm_prepare(ccqp_handle* h);
 ccqp_status ccqp_comm_detach(ccqp_handle* h);
 
+
+/* ---- test vehicle: the ranks of a row-sharded solve emulated on ONE device --------------------
+ * `world` handles created on the same device play ranks 0..world-1: ccqp_debug_emulate_ranks() gives each
+ * 1/world of the SMs and wires the "peer" buffers to each other (no IPC); after ccqp_set_matrix() (each
+ * handle its own row shard) and ccqp_set_projection() on every handle, ccqp_debug_solve_emulated() runs all
+ * ranks inside ONE cooperative launch (CTAs [r*G,(r+1)*G) are rank r).  The kernel code executed is that of
+ * a real sharded solve (fused all-gather into the peers' buffers, {data, epoch} packet all-reduce, the
+ * cross-rank barrier); only the stores do not cross NVLink.  It exists so that the exchange protocol is
+ * covered on single-GPU test boxes.  x_out holds world * n entries (every rank's copy of the solution),
+ * results has world entries. */
+ccqp_status ccqp_debug_emulate_ranks(ccqp_handle* const* handles, int world, int64_t n);
+ccqp_status ccqp_debug_solve_emulated(ccqp_handle* const* handles, int world, int solver, const ccqp_params* params,
+                                      const double* b, const double* x0, const double* uniforms, int64_t n_uniforms,
+                                      double* x_out, int memtype, ccqp_result* results);
+
 #ifdef __cplusplus
 }
 #endif
