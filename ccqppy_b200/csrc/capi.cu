@@ -145,7 +145,7 @@ int env_int(const char* name, int fallback, bool (*ok)(int)) {
     return (int)v;
 }
 bool ok_mult128(int v) { return v >= 128 && v % 128 == 0 && v <= 16384; }
-bool ok_csr_group(int v) { return v == 2 || v == 4 || v == 8 || v == 16 || v == 32; }
+bool ok_csr_group(int v) { return v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32; }
 bool ok_bool(int v) { return v == 0 || v == 1; }
 
 Tiling choose_tiling(const ccqp_handle* h) {
@@ -165,8 +165,8 @@ Tiling choose_tiling(const ccqp_handle* h) {
     const long long work = h->d_val ? (sharded ? rows_ref : h->nnz / 16384) : (rows_ref * n) / 8192;
     t.grid = (int)std::max(1LL, std::min<long long>(std::min<long long>(h->sm_count, rows_ref), std::max(1LL, work)));
     t.accum = 0;
-    if (h->d_val) {     // CSR: no panels of the input vector in shared memory
-        t.CW = 128; t.SW = 128; t.np = 1; t.nseg = 1; t.rows_max = 1;
+    if (h->d_val) {     // CSR: the two panel buffers hold the products of a tile of the entry stream (double buffered)
+        t.CW = kCsrTile; t.SW = kCsrTile; t.np = 1; t.nseg = 1; t.rows_max = 1;
         t.smem = dense_smem_bytes(t.CW, t.rows_max, t.nseg);
         return t;
     }
@@ -209,9 +209,8 @@ void fill_ctx(ccqp_handle* h, DenseCtx& c, const Tiling& t) {
     c.csr_ptr = h->d_ptr; c.csr_idx = h->d_idx; c.csr_val = h->d_val;
     {
         const double mean = h->d_val ? (double)h->nnz / (double)std::max<long long>(h->nrows, 1) : 0.0;
-        // few lanes per row: with 8 warps per SM the loop lives on instruction-level parallelism (16 entries in
-        // flight per lane), so a lane should own tens of entries (sweep: tools/bench_sparse.py with CCQP_CSR_GROUP)
-        c.csr_group = mean >= 1024 ? 32 : mean >= 512 ? 16 : mean >= 256 ? 8 : mean >= 128 ? 4 : 2;
+        // lanes that sum one row out of the shared-memory products: about 8-16 entries per lane
+        c.csr_group = mean >= 256 ? 32 : mean >= 128 ? 16 : mean >= 64 ? 8 : mean >= 24 ? 4 : mean >= 8 ? 2 : 1;
         c.csr_group = env_int("CCQP_CSR_GROUP", c.csr_group, ok_csr_group);
         c.csr_l1 = env_int("CCQP_CSR_L1", 1, ok_bool);
     }

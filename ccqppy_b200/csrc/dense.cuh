@@ -38,7 +38,6 @@ constexpr int kDenseThreads = CCQP_DENSE_THREADS;
 constexpr int kDenseWarps = kDenseThreads / 32;
 constexpr int kUnroll = CCQP_UNROLL;  // 256-bit loads in flight per lane
 constexpr int kMaxWindow = 64;        // SPG non-monotone window
-constexpr int kCsrUnroll = 16;        // CSR mat-vec: stored entries per lane in flight
 
 enum DenseOp : int {
     OP_PGD = 0, OP_APGD = 1, OP_APGD_AR = 2, OP_BBPGD = 3, OP_BBPGDF = 4, OP_SPG = 5, OP_MPRGP = 6,
@@ -237,48 +236,92 @@ __device__ __forceinline__ double dot_seg_generic(const double* __restrict__ aro
     return a0 + a1;
 }
 
-// CSR mat-vec phase (operator-form A: contact-style Hessians D^T M^-1 D are sparse).  A group of
-// csr_group lanes owns a row at a time: values and column indices are streamed coalesced (12 bytes
-// per stored entry, the HBM traffic of the phase), the entries of v are gathered from L2 (ld.cg: v
-// was written by other CTAs earlier in this kernel).  Fixed lane order + shuffle tree => deterministic.
+// CSR mat-vec phase (operator-form A: contact-style Hessians D^T M^-1 D are sparse).
+//
+// The stored entries are treated as ONE stream, independent of the row structure ("CSR-stream"):
+//   * CTAs own nnz-balanced, row-aligned ranges of the stream (dense_body: a binary search in the row
+//     pointers for bid * nnz / G), so a few long rows cannot unbalance the grid;
+//   * a CTA walks its range in tiles of kCsrTile = 256 threads x 16 entries.  Lane l of warp w loads entries
+//     base + 256 u + 32 w + l (u = 0..15): every warp-level load covers 32 CONSECUTIVE entries, so values (LDG.64),
+//     column ids (LDG.32) and, for banded rows, the gather of v (32 consecutive columns = 8 full sectors)
+//     are fully coalesced; 48 loads are in flight per lane and the NEXT tile's values and column ids are
+//     already on their way (register double buffer) while this tile gathers, multiplies and reduces.
+//     v is gathered through L1 (ld.global.ca is legal here: the phase starts behind the sync's acquire and
+//     nobody writes v during it);
+//   * the products go to shared memory (32 KB per tile, double buffered in the two panel buffers the dense path
+//     uses for v), and after ONE barrier groups of csr_group lanes sum the rows that end inside the tile
+//     straight from shared memory (stride csr_group, then a shuffle tree).  A row that continues into the next
+//     tile leaves its partial sum in a carry slot.  Summation order per row: tile by tile, inside a tile lane
+//     by lane + fixed tree: deterministic for a given launch shape, like the dense phase.
+// Algorithmic HBM bytes per mat-vec: 12 per stored entry + 8 (rows + 1) + the vectors.
+constexpr int kCsrE = 16;
+constexpr int kCsrTile = kDenseThreads * kCsrE;
+
 template <class Epi>
 __device__ __forceinline__ void gemv_phase_csr(Kst& k, const DenseCtx& c, const double* v, Epi epi) {
-    const int G = c.csr_group, glane = threadIdx.x & (G - 1), gid = threadIdx.x / G, ngroups = kDenseThreads / G;
-    const int nrows_cta = k.r1 - k.r0;
-    const int trips = (nrows_cta + ngroups - 1) / ngroups;          // uniform over the warp: shuffles below
-    for (int it = 0; it < trips; ++it) {
-        const int lr = it * ngroups + gid;
-        const bool valid = lr < nrows_cta;
-        const int row = k.r0 + lr;
-        long long p0 = 0, p1 = 0;
-        if (valid) { p0 = c.csr_ptr[row - c.row0]; p1 = c.csr_ptr[row - c.row0 + 1]; }
-        // kCsrUnroll stored entries per lane in flight: all column ids and values first, then all gathers, then
-        // the FMAs (the gather depends on the column id, so a short loop would serialise two memory latencies
-        // per entry; with 8 warps per SM the loop needs the instruction-level parallelism)
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-        for (long long base = p0 + glane; base < p1; base += (long long)kCsrUnroll * G) {
-            int j[kCsrUnroll];
-            double w[kCsrUnroll], x[kCsrUnroll];
+    const int tid = threadIdx.x;
+    const int G = c.csr_group, glane = tid & (G - 1), gid = tid / G, ngroups = kDenseThreads / G;
+    const int cr0 = k.r0 - c.row0, cr1 = k.r1 - c.row0;               // this CTA's rows, relative to the shard
+    volatile double* carry_slot = k.sm.scratch;                       // [2]
+    volatile int* rnext_slot = reinterpret_cast<volatile int*>(k.sm.ascratch);   // [2]
+    if (cr1 > cr0) {                                                  // CTA-uniform
+        const long long P0 = c.csr_ptr[cr0], P1 = c.csr_ptr[cr1];
+        if (tid == 0) { carry_slot[0] = 0.0; rnext_slot[0] = cr0; }
+        int jc[kCsrE], jn[kCsrE];
+        double wc[kCsrE], wn[kCsrE];
+        auto load_tile = [&](long long base, int (&j)[kCsrE], double (&w)[kCsrE]) {
 #pragma unroll
-            for (int u = 0; u < kCsrUnroll; ++u) {
-                const long long q = base + (long long)u * G;
-                const bool ok = q < p1;
+            for (int u = 0; u < kCsrE; ++u) {
+                const long long q = base + u * kDenseThreads + tid;
+                const bool ok = q < P1;
                 j[u] = ok ? __ldg(c.csr_idx + q) : 0;
                 w[u] = ok ? ldg_stream(c.csr_val + q) : 0.0;
             }
+        };
+        load_tile(P0, jc, wc);
+        int tile = 0;
+        for (long long t0 = P0;; t0 += kCsrTile, ++tile) {
+            const long long t1 = (t0 + kCsrTile < P1) ? t0 + kCsrTile : P1;
+            const bool more = t1 < P1;
+            if (more) load_tile(t1, jn, wn);                         // next tile's stream: in flight during this tile
+            double* prod = k.sm.vbuf[tile & 1];
+            {
+                double x[kCsrE];
 #pragma unroll
-            for (int u = 0; u < kCsrUnroll; ++u) x[u] = c.csr_l1 ? ld_ca(v + j[u]) : ld_cg(v + j[u]);
+                for (int u = 0; u < kCsrE; ++u) x[u] = c.csr_l1 ? ld_ca(v + jc[u]) : ld_cg(v + jc[u]);
 #pragma unroll
-            for (int u = 0; u < kCsrUnroll; u += 4) {
-                a0 = fma(w[u], x[u], a0);
-                a1 = fma(w[u + 1], x[u + 1], a1);
-                a2 = fma(w[u + 2], x[u + 2], a2);
-                a3 = fma(w[u + 3], x[u + 3], a3);
+                for (int u = 0; u < kCsrE; ++u) prod[u * kDenseThreads + tid] = wc[u] * x[u];
             }
+            __syncthreads();          // products of this tile (and the carry / first row left by the previous tile) are visible
+            const int r_cur = rnext_slot[tile & 1];
+            const double carry_in = carry_slot[tile & 1];
+            for (int kk = 0;; ++kk) {
+                const int r = r_cur + gid + kk * ngroups;
+                long long p0 = 0, p1 = 0;
+                bool active = false;
+                if (r < cr1) { p0 = c.csr_ptr[r]; p1 = c.csr_ptr[r + 1]; active = p0 <= t1; }
+                if (!__any_sync(0xffffffffu, active)) break;         // rows are ordered: nobody in this warp has work left
+                const bool complete = active && p1 <= t1;            // the row ends inside this tile
+                const bool open = active && !complete;               // the one row that continues into the next tile
+                double a0 = 0.0, a1 = 0.0;
+                if (active) {
+                    const long long lo = (p0 > t0 ? p0 : t0) - t0, hi = (p1 < t1 ? p1 : t1) - t0;
+                    long long q = lo + glane;
+                    for (; q + G < hi; q += 2 * G) { a0 += prod[q]; a1 += prod[q + G]; }
+                    if (q < hi) a0 += prod[q];
+                }
+                double acc = a0 + a1;
+                for (int o = G >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                if (glane == 0) {
+                    if (r == r_cur) acc = carry_in + acc;             // earlier tiles' part of the row first
+                    if (complete) epi(c.row0 + r, acc);
+                    else if (open) { carry_slot[(tile + 1) & 1] = acc; rnext_slot[(tile + 1) & 1] = r; }
+                }
+            }
+            if (!more) break;
+#pragma unroll
+            for (int u = 0; u < kCsrE; ++u) { jc[u] = jn[u]; wc[u] = wn[u]; }
         }
-        double acc = (a0 + a1) + (a2 + a3);
-        for (int o = G >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (valid && glane == 0) epi(row, acc);
     }
     k.gemv += 1;
     __syncthreads();
@@ -946,6 +989,16 @@ __device__ __forceinline__ void dense_body(const DenseCtx& c, const int bid, con
     k.gstride = nblk * kDenseThreads;
     k.r0 = c.row0 + (int)(((long long)c.nrows * bid) / nblk);
     k.r1 = c.row0 + (int)(((long long)c.nrows * (bid + 1)) / nblk);
+    if (c.csr_val) {    // CSR: nnz-balanced, row-aligned split (first row whose start is at or beyond bid * nnz / G)
+        const long long nnz = c.csr_ptr[c.nrows];
+        auto first_row_at = [&](long long target) {
+            int lo = 0, hi = c.nrows;                                 // smallest r in [0, nrows] with csr_ptr[r] >= target
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (c.csr_ptr[mid] >= target) hi = mid; else lo = mid + 1; }
+            return lo;
+        };
+        k.r0 = c.row0 + (bid == 0 ? 0 : first_row_at(nnz / nblk * bid + nnz % nblk * bid / nblk));
+        k.r1 = c.row0 + (bid == nblk - 1 ? c.nrows : first_row_at(nnz / nblk * (bid + 1) + nnz % nblk * (bid + 1) / nblk));
+    }
     k.par[0] = k.par[1] = 0u;
     k.mv = k.gemv = k.iters = k.draws = 0;
     k.yq = 0;
