@@ -9,7 +9,12 @@ out of scope), and the problem sizes are arguments, so the same study can be run
 GPU matters.
 
     python -m ccqppy_b200.benchmark disjoint --sizes 3 6 9 12 --trials 100 > study.json
-    python -m ccqppy_b200.benchmark single --sizes 256 1024 4096 --trials 3
+    python -m ccqppy_b200.benchmark single --sizes 256 1024 4096 --trials 3 --generator gpu
+
+`generator="gpu"`: the Wishart Hessian (an n^3 product, the step BEFORE the path) is drawn and multiplied on
+the device in fp64 and handed to `solve()` as a CUDA tensor, which the solver uses in place: no host GEMM, no
+PCIe transfer of A, so the study runs at sizes where a GPU matters.  `"host"` is the reference's NumPy/SciPy
+generator (benchmark_random_ccqp.py:59-62); `"auto"` picks the device from n = 1024 on.
 """
 import argparse
 import json
@@ -25,7 +30,12 @@ class BenchmarkRandomCCQP:
     """benchmark_random_ccqp.py:15-102.  `convex_proj_ops_to_benchmark[t][s]` is the operator of
     constraint type t at problem size s (all types share the sizes of type 0, :25-29)."""
 
-    def __init__(self, num_random_trials, solvers_to_benchmark, convex_proj_ops_to_benchmark, quiet=True):
+    def __init__(self, num_random_trials, solvers_to_benchmark, convex_proj_ops_to_benchmark, quiet=True, generator="auto",
+                 device=None):
+        if generator not in ("auto", "host", "gpu"):
+            raise ValueError("generator must be 'auto', 'host' or 'gpu'")
+        self.generator = generator
+        self.device = device
         self.num_trials = int(num_random_trials)
         self.solvers_to_benchmark = list(solvers_to_benchmark)
         self.convex_proj_ops_to_benchmark = [list(row) for row in convex_proj_ops_to_benchmark]
@@ -37,10 +47,24 @@ class BenchmarkRandomCCQP:
         self._problem_gpu_time = None
         self._problem_num_matrix_vector_mults = None
 
+    def _on_gpu(self, problem_size):
+        return self.generator == "gpu" or (self.generator == "auto" and problem_size >= 1024)
+
     def generate_random_convex_quadratic_func(self, problem_size, seed=1234):
         """A ~ Wishart(df = n, I_n) seeded with `seed`, b = -A x*, x* = 1 - 2 U (:59-62).  The
         reference draws x* from the unseeded global RNG; here it is seeded too, so a
-        study is reproducible."""
+        study is reproducible.  On the device A = G G^T with G an n x n standard normal matrix from
+        torch's seeded generator: the same distribution (that IS the Wishart(n, I) construction), a
+        different random stream than SciPy's."""
+        if self._on_gpu(problem_size):
+            import torch
+            dev = torch.device(self.device if self.device is not None else "cuda")
+            g = torch.Generator(device=dev).manual_seed(int(seed))
+            G = torch.randn((problem_size, problem_size), generator=g, device=dev, dtype=torch.float64)
+            A = G @ G.t()
+            del G
+            x_star = 1 - 2 * torch.rand(problem_size, generator=g, device=dev, dtype=torch.float64)
+            return A, -(A @ x_star)
         rng = np.random.RandomState(seed)
         try:
             from scipy.stats import wishart
@@ -124,20 +148,21 @@ def _solver_set(tol, max_mv, with_mprgp):
     return s
 
 
-def benchmark_single_constraint(problem_sizes=None, num_random_trials=10, desired_tol=1e-5, max_mv_mults=5000):
+def benchmark_single_constraint(problem_sizes=None, num_random_trials=10, desired_tol=1e-5, max_mv_mults=5000, generator="auto"):
     """benchmark_random_ccqp.py:155-183: one operator over the whole vector, six solvers."""
     sizes = np.linspace(2, 12, 10, dtype=int) if problem_sizes is None else np.asarray(problem_sizes, dtype=int)
     ops = [[kind(int(d)) for d in sizes] for kind in
            (ss.IdentityProjOp, ss.LowerBoundProjOp, ss.UpperBoundProjOp, ss.SphereProjOp, ss.BoxProjOp)]
-    return BenchmarkRandomCCQP(num_random_trials, _solver_set(desired_tol, max_mv_mults, False), ops).run()
+    return BenchmarkRandomCCQP(num_random_trials, _solver_set(desired_tol, max_mv_mults, False), ops, generator=generator).run()
 
 
-def benchmark_disjoint_constraints(problem_sizes=None, num_random_trials=100, desired_tol=1e-5, max_mv_mults=5000):
+def benchmark_disjoint_constraints(problem_sizes=None, num_random_trials=100, desired_tol=1e-5, max_mv_mults=5000,
+                                   generator="auto"):
     """benchmark_random_ccqp.py:186-216: disjoint unions of 3-wide blocks, seven solvers."""
     sizes = np.arange(3, 13, 3) if problem_sizes is None else np.asarray(problem_sizes, dtype=int)
     ops = [[ss.DisjointProjOp(*[kind(3)] * (int(d) // 3)) for d in sizes] for kind in
            (ss.IdentityProjOp, ss.LowerBoundProjOp, ss.UpperBoundProjOp, ss.SphereProjOp, ss.BoxProjOp)]
-    return BenchmarkRandomCCQP(num_random_trials, _solver_set(desired_tol, max_mv_mults, True), ops).run()
+    return BenchmarkRandomCCQP(num_random_trials, _solver_set(desired_tol, max_mv_mults, True), ops, generator=generator).run()
 
 
 def main(argv=None):
@@ -147,9 +172,10 @@ def main(argv=None):
     ap.add_argument("--trials", type=int)
     ap.add_argument("--tol", type=float, default=1e-5)
     ap.add_argument("--max-mv", type=int, default=5000)
+    ap.add_argument("--generator", choices=["auto", "host", "gpu"], default="auto")
     a = ap.parse_args(argv)
     fn = benchmark_single_constraint if a.study == "single" else benchmark_disjoint_constraints
-    kw = dict(desired_tol=a.tol, max_mv_mults=a.max_mv)
+    kw = dict(desired_tol=a.tol, max_mv_mults=a.max_mv, generator=a.generator)
     if a.sizes:
         kw["problem_sizes"] = a.sizes
     if a.trials:

@@ -165,8 +165,8 @@ Tiling choose_tiling(const ccqp_handle* h) {
     const long long work = h->d_val ? (sharded ? rows_ref : h->nnz / 16384) : (rows_ref * n) / 8192;
     t.grid = (int)std::max(1LL, std::min<long long>(std::min<long long>(h->sm_count, rows_ref), std::max(1LL, work)));
     t.accum = 0;
-    if (h->d_val) {     // CSR: the two panel buffers hold the products of a tile of the entry stream (double buffered)
-        t.CW = kCsrTile; t.SW = kCsrTile; t.np = 1; t.nseg = 1; t.rows_max = 1;
+    if (h->d_val) {     // CSR: the two panel buffers together are the ring of TMA stages of the entry stream
+        t.CW = kCsrCW; t.SW = kCsrCW; t.np = 1; t.nseg = 1; t.rows_max = 1;
         t.smem = dense_smem_bytes(t.CW, t.rows_max, t.nseg);
         return t;
     }
@@ -210,9 +210,12 @@ void fill_ctx(ccqp_handle* h, DenseCtx& c, const Tiling& t) {
     {
         const double mean = h->d_val ? (double)h->nnz / (double)std::max<long long>(h->nrows, 1) : 0.0;
         // lanes that sum one row out of the shared-memory products: about 8-16 entries per lane
-        c.csr_group = mean >= 256 ? 32 : mean >= 128 ? 16 : mean >= 64 ? 8 : mean >= 24 ? 4 : mean >= 8 ? 2 : 1;
+        // (a tile of 4096 entries should hold about as many rows as there are groups: one pass over the rows)
+        c.csr_group = mean >= 512 ? 32 : mean >= 256 ? 16 : mean >= 128 ? 8 : mean >= 64 ? 4 : mean >= 32 ? 2 : 1;
         c.csr_group = env_int("CCQP_CSR_GROUP", c.csr_group, ok_csr_group);
         c.csr_l1 = env_int("CCQP_CSR_L1", 1, ok_bool);
+        c.csr_tma = ((reinterpret_cast<uintptr_t>(h->d_val) & 15) == 0 && (reinterpret_cast<uintptr_t>(h->d_idx) & 15) == 0) ? 1 : 0;
+        c.csr_tma = std::min(c.csr_tma, env_int("CCQP_CSR_TMA", 1, ok_bool));
     }
     c.b = w + W_B * h->npad; c.x0 = w + W_X0 * h->npad; c.x_out = w + W_XOUT * h->npad;
     c.hook_in = w + W_HIN * h->npad; c.hook_out = w + W_HOUT * h->npad;

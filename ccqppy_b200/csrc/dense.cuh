@@ -65,6 +65,7 @@ struct DenseCtx {
     const double* csr_val;      // [nnz]
     int csr_group;              // lanes that share one row: 2, 4, 8, 16 or 32 (from the mean row length)
     int csr_l1;                 // gather v through L1 (see ld_ca)
+    int csr_tma;                // values and column ids are 16-byte aligned: tiles can be moved by bulk copies
     const double* b;    // [npad]
     const double* x0;   // [npad] (zeros if the caller passed none)
     ProjTable T;
@@ -97,7 +98,7 @@ struct DenseSmem {
     double* vbuf[2];
     double* psum;
     double* scratch;        // kMaxRed*32 doubles
-    uint64_t* mbar;         // 2
+    uint64_t* mbar;         // kNumMbar
     unsigned long long* ascratch;   // 32
 };
 
@@ -110,7 +111,7 @@ __host__ __device__ inline size_t dense_smem_bytes(int CW, int rows_max, int nse
     s += (size_t)rows_max * nseg * 8;
     s += kMaxRed * 32 * 8;
     s += 32 * 8;
-    s += 2 * 8;
+    s += 4 * 8;
     return s + 128;
 }
 
@@ -120,7 +121,7 @@ struct Kst {                // per-thread kernel state
     int bid, nblk;          // this CTA's index in / the size of the rank's grid (blockIdx.x / gridDim.x unless ranks are emulated)
     int gtid, gstride;
     int r0, r1;             // rows of this CTA (global indices)
-    unsigned par[2];        // mbarrier phase parity per buffer
+    unsigned par[4];        // mbarrier phase parity per buffer (dense: 2 panel buffers; CSR: 4 ring stages)
     int yq;                 // next buffer of the mat-vec output pool
     long long mv, gemv, iters, draws;
 };
@@ -241,21 +242,26 @@ __device__ __forceinline__ double dot_seg_generic(const double* __restrict__ aro
 // The stored entries are treated as ONE stream, independent of the row structure ("CSR-stream"):
 //   * CTAs own nnz-balanced, row-aligned ranges of the stream (dense_body: a binary search in the row
 //     pointers for bid * nnz / G), so a few long rows cannot unbalance the grid;
-//   * a CTA walks its range in tiles of kCsrTile = 256 threads x 16 entries.  Lane l of warp w loads entries
-//     base + 256 u + 32 w + l (u = 0..15): every warp-level load covers 32 CONSECUTIVE entries, so values (LDG.64),
-//     column ids (LDG.32) and, for banded rows, the gather of v (32 consecutive columns = 8 full sectors)
-//     are fully coalesced; 48 loads are in flight per lane and the NEXT tile's values and column ids are
-//     already on their way (register double buffer) while this tile gathers, multiplies and reduces.
-//     v is gathered through L1 (ld.global.ca is legal here: the phase starts behind the sync's acquire and
-//     nobody writes v during it);
-//   * the products go to shared memory (32 KB per tile, double buffered in the two panel buffers the dense path
-//     uses for v), and after ONE barrier groups of csr_group lanes sum the rows that end inside the tile
-//     straight from shared memory (stride csr_group, then a shuffle tree).  A row that continues into the next
-//     tile leaves its partial sum in a carry slot.  Summation order per row: tile by tile, inside a tile lane
-//     by lane + fixed tree: deterministic for a given launch shape, like the dense phase.
+//   * the stream is cut into tiles of kCsrTile = 4096 entries at GLOBAL multiples of 4096, and the TMA engine
+//     copies a tile's values (32 KB) and column ids (16 KB) into a ring of kCsrStages shared-memory stages with
+//     two bulk copies and one mbarrier per tile (cp.async.bulk, SASS UBLKCP/SYNCS): up to 4 x 48 KB per SM are
+//     in flight with no register cost, independent of what the warps are doing;
+//   * consuming a tile: every thread takes 16 entries, lane-consecutive (entry u*256 + tid), gathers v through
+//     L1 (ld.global.ca is legal here: the phase starts behind the sync's acquire and nobody writes v during it;
+//     for banded rows a warp-level gather covers 32 consecutive columns = 8 full sectors), multiplies and writes
+//     the products IN PLACE over the values; after one barrier groups of csr_group lanes sum the rows that end
+//     inside the tile straight from shared memory (stride csr_group, then a shuffle tree).  A row that continues
+//     into the next tile leaves its partial sum in a carry slot.  A second barrier frees the stage, which thread 0
+//     refills at once with tile t + kCsrStages.
+//   Summation order per row: tile by tile, inside a tile lane by lane + fixed tree; tile boundaries do not depend
+//   on the launch shape.  The stream's final tile, if its length is not a multiple of 4 entries (bulk copies move
+//   multiples of 16 bytes), is read with ordinary loads.
 // Algorithmic HBM bytes per mat-vec: 12 per stored entry + 8 (rows + 1) + the vectors.
 constexpr int kCsrE = 16;
 constexpr int kCsrTile = kDenseThreads * kCsrE;
+constexpr int kCsrStages = 4;
+constexpr int kCsrStageBytes = kCsrTile * 12;         // values, then column ids
+constexpr int kCsrCW = kCsrStages * kCsrStageBytes / 16;   // "panel width" that makes the two panel buffers hold the ring
 
 template <class Epi>
 __device__ __forceinline__ void gemv_phase_csr(Kst& k, const DenseCtx& c, const double* v, Epi epi) {
@@ -264,37 +270,55 @@ __device__ __forceinline__ void gemv_phase_csr(Kst& k, const DenseCtx& c, const 
     const int cr0 = k.r0 - c.row0, cr1 = k.r1 - c.row0;               // this CTA's rows, relative to the shard
     volatile double* carry_slot = k.sm.scratch;                       // [2]
     volatile int* rnext_slot = reinterpret_cast<volatile int*>(k.sm.ascratch);   // [2]
-    if (cr1 > cr0) {                                                  // CTA-uniform
-        const long long P0 = c.csr_ptr[cr0], P1 = c.csr_ptr[cr1];
-        if (tid == 0) { carry_slot[0] = 0.0; rnext_slot[0] = cr0; }
-        int jc[kCsrE], jn[kCsrE];
-        double wc[kCsrE], wn[kCsrE];
-        auto load_tile = [&](long long base, int (&j)[kCsrE], double (&w)[kCsrE]) {
-#pragma unroll
-            for (int u = 0; u < kCsrE; ++u) {
-                const long long q = base + u * kDenseThreads + tid;
-                const bool ok = q < P1;
-                j[u] = ok ? __ldg(c.csr_idx + q) : 0;
-                w[u] = ok ? ldg_stream(c.csr_val + q) : 0.0;
-            }
+    unsigned char* ring = reinterpret_cast<unsigned char*>(k.sm.vbuf[0]);
+    const long long P0 = cr1 > cr0 ? c.csr_ptr[cr0] : 0, P1 = cr1 > cr0 ? c.csr_ptr[cr1] : 0;
+    if (P1 > P0) {                                                    // CTA-uniform
+        const long long nnz = c.csr_ptr[c.nrows];
+        const long long g0 = P0 / kCsrTile;
+        const int nt = (int)((P1 - 1) / kCsrTile - g0) + 1;
+        auto tile_count = [&](int t) { const long long T = (g0 + t) * kCsrTile; return (int)(nnz - T < kCsrTile ? nnz - T : kCsrTile); };
+        auto issue = [&](int t) {                                     // thread 0 only
+            const int cnt = tile_count(t);
+            if ((cnt & 3) || !c.csr_tma) return;                      // ragged final tile of the stream: ordinary loads at consume time
+            const int st = t % kCsrStages;
+            const long long T = (g0 + t) * kCsrTile;
+            unsigned char* dst = ring + (size_t)st * kCsrStageBytes;
+            mbar_expect_tx(&k.sm.mbar[st], (uint32_t)cnt * 12u);
+            bulk_g2s(dst, c.csr_val + T, (uint32_t)cnt * 8u, &k.sm.mbar[st]);
+            bulk_g2s(dst + kCsrTile * 8, c.csr_idx + T, (uint32_t)cnt * 4u, &k.sm.mbar[st]);
         };
-        load_tile(P0, jc, wc);
-        int tile = 0;
-        for (long long t0 = P0;; t0 += kCsrTile, ++tile) {
-            const long long t1 = (t0 + kCsrTile < P1) ? t0 + kCsrTile : P1;
-            const bool more = t1 < P1;
-            if (more) load_tile(t1, jn, wn);                         // next tile's stream: in flight during this tile
-            double* prod = k.sm.vbuf[tile & 1];
-            {
+        if (tid == 0) {
+            carry_slot[0] = 0.0; rnext_slot[0] = cr0;
+            fence_proxy_async();
+            for (int t = 0; t < nt && t < kCsrStages; ++t) issue(t);
+        }
+        for (int t = 0; t < nt; ++t) {
+            const int st = t % kCsrStages;
+            const long long T = (g0 + t) * kCsrTile;
+            const int cnt = tile_count(t);
+            double* prod = reinterpret_cast<double*>(ring + (size_t)st * kCsrStageBytes);
+            const int* idx = reinterpret_cast<const int*>(ring + (size_t)st * kCsrStageBytes + kCsrTile * 8);
+            if ((cnt & 3) || !c.csr_tma) {                            // CTA-uniform
+                for (int q = tid; q < cnt; q += kDenseThreads) {
+                    const double x = c.csr_l1 ? ld_ca(v + __ldg(c.csr_idx + T + q)) : ld_cg(v + __ldg(c.csr_idx + T + q));
+                    prod[q] = ldg_stream(c.csr_val + T + q) * x;
+                }
+            } else {
+                mbar_wait(&k.sm.mbar[st], k.par[st]);
+                k.par[st] ^= 1u;
+                int j[kCsrE];
                 double x[kCsrE];
 #pragma unroll
-                for (int u = 0; u < kCsrE; ++u) x[u] = c.csr_l1 ? ld_ca(v + jc[u]) : ld_cg(v + jc[u]);
+                for (int u = 0; u < kCsrE; ++u) { const int q = u * kDenseThreads + tid; j[u] = q < cnt ? idx[q] : 0; }
 #pragma unroll
-                for (int u = 0; u < kCsrE; ++u) prod[u * kDenseThreads + tid] = wc[u] * x[u];
+                for (int u = 0; u < kCsrE; ++u) x[u] = c.csr_l1 ? ld_ca(v + j[u]) : ld_cg(v + j[u]);
+#pragma unroll
+                for (int u = 0; u < kCsrE; ++u) { const int q = u * kDenseThreads + tid; if (q < cnt) prod[q] *= x[u]; }
             }
             __syncthreads();          // products of this tile (and the carry / first row left by the previous tile) are visible
-            const int r_cur = rnext_slot[tile & 1];
-            const double carry_in = carry_slot[tile & 1];
+            const long long t0 = T > P0 ? T : P0, t1 = T + cnt < P1 ? T + cnt : P1;     // this CTA's entries of the tile
+            const int r_cur = rnext_slot[t & 1];
+            const double carry_in = carry_slot[t & 1];
             for (int kk = 0;; ++kk) {
                 const int r = r_cur + gid + kk * ngroups;
                 long long p0 = 0, p1 = 0;
@@ -305,8 +329,8 @@ __device__ __forceinline__ void gemv_phase_csr(Kst& k, const DenseCtx& c, const 
                 const bool open = active && !complete;               // the one row that continues into the next tile
                 double a0 = 0.0, a1 = 0.0;
                 if (active) {
-                    const long long lo = (p0 > t0 ? p0 : t0) - t0, hi = (p1 < t1 ? p1 : t1) - t0;
-                    long long q = lo + glane;
+                    const int lo = (int)((p0 > t0 ? p0 : t0) - T), hi = (int)((p1 < t1 ? p1 : t1) - T);
+                    int q = lo + glane;
                     for (; q + G < hi; q += 2 * G) { a0 += prod[q]; a1 += prod[q + G]; }
                     if (q < hi) a0 += prod[q];
                 }
@@ -315,13 +339,14 @@ __device__ __forceinline__ void gemv_phase_csr(Kst& k, const DenseCtx& c, const 
                 if (glane == 0) {
                     if (r == r_cur) acc = carry_in + acc;             // earlier tiles' part of the row first
                     if (complete) epi(c.row0 + r, acc);
-                    else if (open) { carry_slot[(tile + 1) & 1] = acc; rnext_slot[(tile + 1) & 1] = r; }
+                    else if (open) { carry_slot[(t + 1) & 1] = acc; rnext_slot[(t + 1) & 1] = r; }
                 }
             }
-            if (!more) break;
-#pragma unroll
-            for (int u = 0; u < kCsrE; ++u) { jc[u] = jn[u]; wc[u] = wn[u]; }
+            __syncthreads();          // every thread is done with the stage: it can be refilled
+            if (tid == 0 && t + kCsrStages < nt) { fence_proxy_async(); issue(t + kCsrStages); }
         }
+    } else {
+        for (int r = cr0 + tid; r < cr1; r += kDenseThreads) epi(c.row0 + r, 0.0);     // a range of empty rows
     }
     k.gemv += 1;
     __syncthreads();
@@ -999,12 +1024,11 @@ __device__ __forceinline__ void dense_body(const DenseCtx& c, const int bid, con
         k.r0 = c.row0 + (bid == 0 ? 0 : first_row_at(nnz / nblk * bid + nnz % nblk * bid / nblk));
         k.r1 = c.row0 + (bid == nblk - 1 ? c.nrows : first_row_at(nnz / nblk * (bid + 1) + nnz % nblk * (bid + 1) / nblk));
     }
-    k.par[0] = k.par[1] = 0u;
+    k.par[0] = k.par[1] = k.par[2] = k.par[3] = 0u;
     k.mv = k.gemv = k.iters = k.draws = 0;
     k.yq = 0;
     if (threadIdx.x == 0) {
-        mbar_init(&k.sm.mbar[0], 1);
-        mbar_init(&k.sm.mbar[1], 1);
+        for (int i = 0; i < 4; ++i) mbar_init(&k.sm.mbar[i], 1);
         mbar_fence_init();
     }
     __syncthreads();

@@ -38,6 +38,7 @@ warnings.simplefilter("ignore")
 import ccqppy.solvers as ref_solvers              # noqa: E402  (the reference)
 import ccqppy.solution_spaces as ref_ss           # noqa: E402
 import ccqppy.problem_suite as ref_suite          # noqa: E402
+assert os.path.realpath(ref_solvers.__file__).startswith("/root/reference/"), "the name ccqppy must be the reference here"
 
 import problems as pr                              # noqa: E402  (tests/problems.py)
 from oracle import ccqp_oracle as orc              # noqa: E402

@@ -322,3 +322,35 @@ def test_pipelined_solves_equal_synchronous_solves():
             assert np.array_equal(np.asarray(r.solution), np.asarray(s.solution))
     with pytest.raises(ValueError):
         SolvePipeline(solvers.CCQPSolverSPG(1e-6, 100)).submit(probs[0][0], probs[0][1])
+
+
+def test_benchmark_driver_with_the_gpu_generator():
+    """Row f-2: the study at a size where the GPU matters, Hessians generated on the device and used in place
+    (no host GEMM, no PCIe copy of A).  Checked through the reference's own residual recomputed with torch."""
+    import torch
+    from ccqppy_b200 import benchmark, solution_spaces as ss, solvers
+    n = 1536
+    ops = [[ss.BoxProjOp(n)], [ss.DisjointProjOp(*[ss.SphereProjOp(3)] * (n // 3))]]
+    study = benchmark.BenchmarkRandomCCQP(2, [solvers.CCQPSolverBBPGD(1e-5, 5000), solvers.CCQPSolverMPRGP(1e-5, 5000)], ops,
+                                          generator="gpu").run()
+    A, b = study.generate_random_convex_quadratic_func(n, 0)
+    assert A.is_cuda and b.is_cuda and A.dtype == torch.float64
+    A2, _ = study.generate_random_convex_quadratic_func(n, 0)
+    assert torch.equal(A, A2)                                                    # seeded: a study is reproducible
+    assert float((A - A.t()).abs().max()) == 0.0 or float((A - A.t()).abs().max()) < 1e-9 * float(A.abs().max())
+    assert study.problem_converged.shape == (2, 2, 1, 2)
+    s = solvers.CCQPSolverBBPGD(1e-5, 5000)
+    s.quiet = True
+    s.solve(A, b, convex_proj_op=ops[0][0])
+    assert s.solution.is_cuda                                                    # stayed on the device end to end
+    assert int(s.solution_num_matrix_vector_multiplications) == int(study.problem_num_matrix_vector_mults[0, 0, 0, 0])
+    if s.solution_converged:
+        x = s.solution
+        g = A @ x + b
+        assert float((x - (x - 1e-6 * g).clamp(-1, 1)).norm()) / (3 * n * 1e-6) < 1e-5 * 1.01
+    summ = study.summary()
+    assert summ["sizes"] == [n] and len(summ["solvers"]) == 2
+    # "auto" keeps the reference's host generator for the reference's own (tiny) sizes
+    small = benchmark.BenchmarkRandomCCQP(1, [], [[ss.BoxProjOp(6)]])
+    As, _ = small.generate_random_convex_quadratic_func(6, 0)
+    assert isinstance(As, np.ndarray)

@@ -27,12 +27,20 @@ _stub = tempfile.mkdtemp(prefix="mplstub")
 os.makedirs(os.path.join(_stub, "matplotlib"))
 for _f in ("__init__.py", "pyplot.py"):
     open(os.path.join(_stub, "matplotlib", _f), "w").close()
+# The repository's own drop-in package is ALSO called `ccqppy`: make sure the name resolves to the reference while it is
+# imported here, check that it did, and take the name out of sys.modules / sys.path again so that later tests get the shim.
+for _k in [m for m in sys.modules if m == "ccqppy" or m.startswith("ccqppy.")]:
+    del sys.modules[_k]
 sys.path.insert(0, _stub)
 sys.path.insert(0, REF_SRC)
 with warnings.catch_warnings():
     warnings.simplefilter("ignore")
     import ccqppy.solvers as ref_solvers                   # noqa: E402  (the reference)
     import ccqppy.solution_spaces as ref_ss                # noqa: E402
+assert os.path.realpath(ref_solvers.__file__).startswith(os.path.realpath(REF_SRC)), ref_solvers.__file__
+for _k in [m for m in sys.modules if m == "ccqppy" or m.startswith("ccqppy.")]:
+    del sys.modules[_k]
+sys.path.remove(REF_SRC)
 
 
 def ref_op(tab):
