@@ -48,7 +48,7 @@ struct ccqp_handle {
     const long long* d_ptr = nullptr;
     const int* d_idx = nullptr;
     const double* d_val = nullptr;
-    DevBuf ptr_own, idx_own, val_own;
+    DevBuf ptr_own, idx_own, val_own, tile_row;   // tile_row: see csr_tile_rows_kernel
     long long nnz = 0;
     bool have_matrix() const { return dA != nullptr || d_val != nullptr; }
     long long n = 0, lda = 0, row0 = 0, nrows = 0;
@@ -79,6 +79,19 @@ struct ccqp_handle {
 };
 
 namespace {
+
+// csr_tile_row[g] = the row that contains stored entry g * kCsrTile (the last row whose pointer is <= that entry;
+// nrows when the entry lies beyond the end of the stream): which rows a tile of the entry stream touches, without a
+// search inside the mat-vec.  One thread per tile boundary, once per matrix.
+__global__ void csr_tile_rows_kernel(const long long* __restrict__ ptr, int nrows, int* __restrict__ tile_row, int count) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= count) return;
+    const long long nnz = ptr[nrows], E = (long long)g * kCsrTile;
+    if (E >= nnz) { tile_row[g] = nrows; return; }
+    int lo = 0, hi = nrows;                                    // first r with ptr[r] > E
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (ptr[mid] > E) hi = mid; else lo = mid + 1; }
+    tile_row[g] = lo - 1;
+}
 
 const char* kStatusText[] = {
     "ok", "invalid argument", "no CUDA device (this library has no CPU path)", "CUDA runtime error",
@@ -166,7 +179,7 @@ Tiling choose_tiling(const ccqp_handle* h) {
     t.grid = (int)std::max(1LL, std::min<long long>(std::min<long long>(h->sm_count, rows_ref), std::max(1LL, work)));
     t.accum = 0;
     if (h->d_val) {     // CSR: the two panel buffers together are the ring of TMA stages of the entry stream
-        t.CW = kCsrCW; t.SW = kCsrCW; t.np = 1; t.nseg = 1; t.rows_max = 1;
+        t.CW = kCsrCW; t.SW = kCsrCW; t.np = 1; t.nseg = 1; t.rows_max = kCsrRowsMax;   // (the psum region holds the row-pointer windows)
         t.smem = dense_smem_bytes(t.CW, t.rows_max, t.nseg);
         return t;
     }
@@ -216,6 +229,7 @@ void fill_ctx(ccqp_handle* h, DenseCtx& c, const Tiling& t) {
         c.csr_l1 = env_int("CCQP_CSR_L1", 1, ok_bool);
         c.csr_tma = ((reinterpret_cast<uintptr_t>(h->d_val) & 15) == 0 && (reinterpret_cast<uintptr_t>(h->d_idx) & 15) == 0) ? 1 : 0;
         c.csr_tma = std::min(c.csr_tma, env_int("CCQP_CSR_TMA", 1, ok_bool));
+        c.csr_tile_row = h->tile_row.as<int>();
     }
     c.b = w + W_B * h->npad; c.x0 = w + W_X0 * h->npad; c.x_out = w + W_XOUT * h->npad;
     c.hook_in = w + W_HIN * h->npad; c.hook_out = w + W_HOUT * h->npad;
@@ -243,7 +257,7 @@ void fill_ctx(ccqp_handle* h, DenseCtx& c, const Tiling& t) {
     c.evict_first = env_int("CCQP_EVICT_FIRST", c.evict_first, ok_bool);
 }
 
-constexpr int op_slot(int op) { return op < 100 ? op : 7 + (op - 100); }
+constexpr int op_slot(int op) { return op < 100 ? op : 7 + (op - 100); }   // OP_PROJGRAD -> bit 10
 
 template <int OP>
 ccqp_status launch_dense(ccqp_handle* h, DenseCtx& c, const Tiling& t, bool cooperative) {
@@ -331,7 +345,7 @@ ccqp_status ccqp_destroy(ccqp_handle* h) {
     if (h->world > 1 && !h->emulated) ccqp_comm_detach(h);
     DevBuf* bufs[] = {&h->a_own, &h->lo, &h->hi, &h->ekind, &h->bkind, &h->boff, &h->bdim, &h->bpar, &h->small_ids,
                       &h->big_ids, &h->work, &h->partials, &h->flags, &h->out_dev, &h->uniforms,
-                      &h->batched_ws, &h->dbg, &h->ptr_own, &h->idx_own, &h->val_own, &h->emu_ctx};
+                      &h->batched_ws, &h->dbg, &h->ptr_own, &h->idx_own, &h->val_own, &h->emu_ctx, &h->tile_row};
     for (DevBuf* b : bufs) b->release();
     if (h->out_host) cudaFreeHost(h->out_host);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -409,6 +423,11 @@ ccqp_status ccqp_set_matrix_csr(ccqp_handle* h, const int64_t* indptr, const int
         CU(h, cudaStreamSynchronize(h->stream));       // pageable host arrays may go away
         h->d_ptr = h->ptr_own.as<long long>(); h->d_idx = h->idx_own.as<int>(); h->d_val = h->val_own.as<double>();
     }
+    const int count = (int)((nnz + kCsrTile - 1) / kCsrTile) + 1;
+    CU(h, h->tile_row.ensure((size_t)count * 4));
+    csr_tile_rows_kernel<<<(count + 255) / 256, 256, 0, h->stream>>>(h->d_ptr, (int)n_rows, h->tile_row.as<int>(), count);
+    CU(h, cudaGetLastError());
+    h->launches += 1;
     return CCQP_OK;
 }
 
@@ -679,6 +698,37 @@ ccqp_status ccqp_normal(ccqp_handle* h, const double* x, double* out, int memtyp
     if (!h) return CCQP_ERR_INVALID_ARG;
     if (h->has_cone_ref) return CCQP_ERR_NORMAL_NOT_IMPLEMENTED;
     return run_hook(h, OP_NORMAL, x, out, h->proj_n, h->proj_n, memtype);
+}
+
+ccqp_status ccqp_projected_gradient(ccqp_handle* h, const double* x, const double* g, double* free_out, double* chopped_out,
+                                    int memtype) {
+    if (!h || !x || !g || !free_out || !chopped_out) return CCQP_ERR_INVALID_ARG;
+    if (!h->have_proj) return CCQP_ERR_NOT_READY;
+    if (h->nsmall + h->nbig > 0) return h->has_cone_ref ? CCQP_ERR_NORMAL_NOT_IMPLEMENTED : CCQP_ERR_UNSUPPORTED;   // Sphere / Cone / SOC leaves
+    if (h->world > 1) return CCQP_ERR_UNSUPPORTED;
+    CU(h, cudaSetDevice(h->device));
+    if (!h->have_matrix()) { h->n = h->proj_n; h->row0 = 0; h->nrows = h->proj_n; }
+    else if (h->proj_n != h->n) return CCQP_ERR_INVALID_ARG;
+    ccqp_status st = ensure_work(h);
+    if (st != CCQP_OK) return st;
+    const long long n = h->proj_n, npad = h->npad;
+    double* w = reinterpret_cast<double*>(h->work.as<char>() + kSymVecOff);
+    CU(h, cudaMemsetAsync(w + W_HIN * npad, 0, (size_t)2 * npad * 8, h->stream));
+    CU(h, cudaMemsetAsync(w + W_VEC0 * npad, 0, (size_t)3 * npad * 8, h->stream));
+    if ((st = copy_in(h, w + W_HIN * npad, x, n, memtype)) != CCQP_OK) return st;
+    if ((st = copy_in(h, w + W_VEC0 * npad, g, n, memtype)) != CCQP_OK) return st;
+    Tiling t;
+    t.grid = (int)std::max<long long>(1, std::min<long long>(h->sm_count, n)); t.CW = 128; t.SW = 128; t.np = 1; t.nseg = 1; t.rows_max = 1;
+    t.accum = 0; t.smem = dense_smem_bytes(128, 1, 1);
+    DenseCtx c;
+    fill_ctx(h, c, t);
+    c.csr_val = nullptr;              // the hooks never touch the matrix
+    if ((st = launch_dense<OP_NORMAL>(h, c, t, false)) != CCQP_OK) return st;
+    if ((st = launch_dense<OP_PROJGRAD>(h, c, t, false)) != CCQP_OK) return st;
+    if ((st = copy_out(h, free_out, c.vec[1], n, memtype)) != CCQP_OK) return st;
+    if ((st = copy_out(h, chopped_out, c.vec[2], n, memtype)) != CCQP_OK) return st;
+    CU(h, cudaStreamSynchronize(h->stream));
+    return CCQP_OK;
 }
 
 ccqp_status ccqp_solve_batched(ccqp_handle* h, int solver, const ccqp_params* params, int64_t batch, int64_t n,

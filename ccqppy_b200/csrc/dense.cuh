@@ -41,7 +41,7 @@ constexpr int kMaxWindow = 64;        // SPG non-monotone window
 
 enum DenseOp : int {
     OP_PGD = 0, OP_APGD = 1, OP_APGD_AR = 2, OP_BBPGD = 3, OP_BBPGDF = 4, OP_SPG = 5, OP_MPRGP = 6,
-    OP_GEMV = 100, OP_PROJECT = 101, OP_NORMAL = 102
+    OP_GEMV = 100, OP_PROJECT = 101, OP_NORMAL = 102, OP_PROJGRAD = 103
 };
 
 struct DenseOut {          // written by CTA 0 / thread 0
@@ -66,6 +66,7 @@ struct DenseCtx {
     int csr_group;              // lanes that share one row: 2, 4, 8, 16 or 32 (from the mean row length)
     int csr_l1;                 // gather v through L1 (see ld_ca)
     int csr_tma;                // values and column ids are 16-byte aligned: tiles can be moved by bulk copies
+    const int* csr_tile_row;    // [ceil(nnz / 4096) + 1]: the row that contains entry g * 4096 (nrows beyond the end)
     const double* b;    // [npad]
     const double* x0;   // [npad] (zeros if the caller passed none)
     ProjTable T;
@@ -244,15 +245,19 @@ __device__ __forceinline__ double dot_seg_generic(const double* __restrict__ aro
 //     pointers for bid * nnz / G), so a few long rows cannot unbalance the grid;
 //   * the stream is cut into tiles of kCsrTile = 4096 entries at GLOBAL multiples of 4096, and the TMA engine
 //     copies a tile's values (32 KB) and column ids (16 KB) into a ring of kCsrStages shared-memory stages with
-//     two bulk copies and one mbarrier per tile (cp.async.bulk, SASS UBLKCP/SYNCS): up to 4 x 48 KB per SM are
-//     in flight with no register cost, independent of what the warps are doing;
+//     two bulk copies and one mbarrier per tile (cp.async.bulk with an L2 evict-first hint, SASS UBLKCP/SYNCS):
+//     up to 3 x 48 KB per SM are in flight with no register cost, independent of what the warps are doing, and
+//     the stream does not push the vectors (the gather targets) out of L2;
+//   * csr_tile_row[g] (computed once per matrix, ccqp_set_matrix_csr) names the row that contains entry g * 4096,
+//     so the rows a tile touches are known without a search: their row pointers are fetched with one coalesced
+//     load into a shared-memory window while the gather is in flight;
 //   * consuming a tile: every thread takes 16 entries, lane-consecutive (entry u*256 + tid), gathers v through
 //     L1 (ld.global.ca is legal here: the phase starts behind the sync's acquire and nobody writes v during it;
 //     for banded rows a warp-level gather covers 32 consecutive columns = 8 full sectors), multiplies and writes
-//     the products IN PLACE over the values; after one barrier groups of csr_group lanes sum the rows that end
-//     inside the tile straight from shared memory (stride csr_group, then a shuffle tree).  A row that continues
-//     into the next tile leaves its partial sum in a carry slot.  A second barrier frees the stage, which thread 0
-//     refills at once with tile t + kCsrStages.
+//     the products IN PLACE over the values; after ONE barrier per tile groups of csr_group lanes sum the rows
+//     that end inside the tile straight from shared memory (stride csr_group, then a shuffle tree).  A row that
+//     continues into the next tile leaves its partial sum in a carry slot.  The barrier of tile t+1 also proves
+//     that everybody is done with tile t, whose stage thread 0 then refills with tile t + kCsrStages.
 //   Summation order per row: tile by tile, inside a tile lane by lane + fixed tree; tile boundaries do not depend
 //   on the launch shape.  The stream's final tile, if its length is not a multiple of 4 entries (bulk copies move
 //   multiples of 16 bytes), is read with ordinary loads.
@@ -262,14 +267,23 @@ constexpr int kCsrTile = kDenseThreads * kCsrE;
 constexpr int kCsrStages = 4;
 constexpr int kCsrStageBytes = kCsrTile * 12;         // values, then column ids
 constexpr int kCsrCW = kCsrStages * kCsrStageBytes / 16;   // "panel width" that makes the two panel buffers hold the ring
+constexpr int kCsrWin = kDenseThreads + 1;            // row pointers of a tile kept in shared memory
+constexpr int kCsrRowsMax = 2 * kCsrWin + 8;          // "rows_max" that makes the psum region hold two such windows
+
+__device__ __forceinline__ void bulk_g2s_evict_first(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
+}
 
 template <class Epi>
 __device__ __forceinline__ void gemv_phase_csr(Kst& k, const DenseCtx& c, const double* v, Epi epi) {
     const int tid = threadIdx.x;
     const int G = c.csr_group, glane = tid & (G - 1), gid = tid / G, ngroups = kDenseThreads / G;
     const int cr0 = k.r0 - c.row0, cr1 = k.r1 - c.row0;               // this CTA's rows, relative to the shard
-    volatile double* carry_slot = k.sm.scratch;                       // [2]
-    volatile int* rnext_slot = reinterpret_cast<volatile int*>(k.sm.ascratch);   // [2]
+    volatile double* carry_slot = k.sm.scratch;                       // [2], by tile parity
+    long long* win = reinterpret_cast<long long*>(k.sm.psum);         // [2][kCsrWin], by tile parity
     unsigned char* ring = reinterpret_cast<unsigned char*>(k.sm.vbuf[0]);
     const long long P0 = cr1 > cr0 ? c.csr_ptr[cr0] : 0, P1 = cr1 > cr0 ? c.csr_ptr[cr1] : 0;
     if (P1 > P0) {                                                    // CTA-uniform
@@ -284,18 +298,28 @@ __device__ __forceinline__ void gemv_phase_csr(Kst& k, const DenseCtx& c, const 
             const long long T = (g0 + t) * kCsrTile;
             unsigned char* dst = ring + (size_t)st * kCsrStageBytes;
             mbar_expect_tx(&k.sm.mbar[st], (uint32_t)cnt * 12u);
-            bulk_g2s(dst, c.csr_val + T, (uint32_t)cnt * 8u, &k.sm.mbar[st]);
-            bulk_g2s(dst + kCsrTile * 8, c.csr_idx + T, (uint32_t)cnt * 4u, &k.sm.mbar[st]);
+            bulk_g2s_evict_first(dst, c.csr_val + T, (uint32_t)cnt * 8u, &k.sm.mbar[st]);
+            bulk_g2s_evict_first(dst + kCsrTile * 8, c.csr_idx + T, (uint32_t)cnt * 4u, &k.sm.mbar[st]);
         };
         if (tid == 0) {
-            carry_slot[0] = 0.0; rnext_slot[0] = cr0;
+            carry_slot[0] = 0.0;
             fence_proxy_async();
-            for (int t = 0; t < nt && t < kCsrStages; ++t) issue(t);
+            for (int t = 0; t < nt && t < kCsrStages - 1; ++t) issue(t);
         }
         for (int t = 0; t < nt; ++t) {
             const int st = t % kCsrStages;
             const long long T = (g0 + t) * kCsrTile;
             const int cnt = tile_count(t);
+            const long long t0 = T > P0 ? T : P0, t1 = T + cnt < P1 ? T + cnt : P1;     // this CTA's entries of the tile
+            // rows of the tile: r_cur (open since the previous tile, or this CTA's first row) ... r_last
+            int r_cur = t == 0 ? cr0 : c.csr_tile_row[g0 + t], r_last = c.csr_tile_row[g0 + t + 1];
+            if (r_last > cr1 - 1 || T + cnt >= P1) r_last = cr1 - 1;
+            const int nrows_t = r_last - r_cur + 1;
+            long long* pw = win + (t & 1) * kCsrWin;
+            // row pointers r_cur .. r_cur + 256 of this tile -> shared window: one coalesced load, issued here, stored
+            // after the gather has been issued (so the loads travel together)
+            const long long pv = r_cur + tid <= cr1 ? c.csr_ptr[r_cur + tid] : 0;
+            const long long pv_last = (tid == 0 && r_cur + kDenseThreads <= cr1) ? c.csr_ptr[r_cur + kDenseThreads] : 0;
             double* prod = reinterpret_cast<double*>(ring + (size_t)st * kCsrStageBytes);
             const int* idx = reinterpret_cast<const int*>(ring + (size_t)st * kCsrStageBytes + kCsrTile * 8);
             if ((cnt & 3) || !c.csr_tma) {                            // CTA-uniform
@@ -312,21 +336,26 @@ __device__ __forceinline__ void gemv_phase_csr(Kst& k, const DenseCtx& c, const 
                 for (int u = 0; u < kCsrE; ++u) { const int q = u * kDenseThreads + tid; j[u] = q < cnt ? idx[q] : 0; }
 #pragma unroll
                 for (int u = 0; u < kCsrE; ++u) x[u] = c.csr_l1 ? ld_ca(v + j[u]) : ld_cg(v + j[u]);
+                pw[tid] = pv;
+                if (tid == 0) pw[kDenseThreads] = pv_last;
 #pragma unroll
                 for (int u = 0; u < kCsrE; ++u) { const int q = u * kDenseThreads + tid; if (q < cnt) prod[q] *= x[u]; }
             }
-            __syncthreads();          // products of this tile (and the carry / first row left by the previous tile) are visible
-            const long long t0 = T > P0 ? T : P0, t1 = T + cnt < P1 ? T + cnt : P1;     // this CTA's entries of the tile
-            const int r_cur = rnext_slot[t & 1];
+            if ((cnt & 3) || !c.csr_tma) { pw[tid] = pv; if (tid == 0) pw[kDenseThreads] = pv_last; }
+            __syncthreads();          // products + row-pointer window of this tile and the carry of the previous one are visible;
+                                      // everybody has finished the previous tile, whose stage can be refilled
+            if (tid == 0 && t >= 1 && t - 1 + kCsrStages < nt) { fence_proxy_async(); issue(t - 1 + kCsrStages); }
+            if (tid == 0 && t == 0 && kCsrStages - 1 < nt) { fence_proxy_async(); issue(kCsrStages - 1); }
             const double carry_in = carry_slot[t & 1];
-            for (int kk = 0;; ++kk) {
-                const int r = r_cur + gid + kk * ngroups;
+            for (int kk = 0; kk * ngroups < nrows_t; ++kk) {          // CTA-uniform trip count
+                const int i = gid + kk * ngroups, r = r_cur + i;
+                const bool active = i < nrows_t;
                 long long p0 = 0, p1 = 0;
-                bool active = false;
-                if (r < cr1) { p0 = c.csr_ptr[r]; p1 = c.csr_ptr[r + 1]; active = p0 <= t1; }
-                if (!__any_sync(0xffffffffu, active)) break;         // rows are ordered: nobody in this warp has work left
+                if (active) {
+                    if (i + 1 < kCsrWin) { p0 = pw[i]; p1 = pw[i + 1]; }
+                    else { p0 = c.csr_ptr[r]; p1 = c.csr_ptr[r + 1]; }
+                }
                 const bool complete = active && p1 <= t1;            // the row ends inside this tile
-                const bool open = active && !complete;               // the one row that continues into the next tile
                 double a0 = 0.0, a1 = 0.0;
                 if (active) {
                     const int lo = (int)((p0 > t0 ? p0 : t0) - T), hi = (int)((p1 < t1 ? p1 : t1) - T);
@@ -336,14 +365,12 @@ __device__ __forceinline__ void gemv_phase_csr(Kst& k, const DenseCtx& c, const 
                 }
                 double acc = a0 + a1;
                 for (int o = G >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-                if (glane == 0) {
-                    if (r == r_cur) acc = carry_in + acc;             // earlier tiles' part of the row first
+                if (glane == 0 && active) {
+                    if (i == 0) acc = carry_in + acc;                 // earlier tiles' part of the row first
                     if (complete) epi(c.row0 + r, acc);
-                    else if (open) { carry_slot[(t + 1) & 1] = acc; rnext_slot[(t + 1) & 1] = r; }
+                    else carry_slot[(t + 1) & 1] = acc;               // the one row that continues into the next tile (r_last)
                 }
             }
-            __syncthreads();          // every thread is done with the stage: it can be refilled
-            if (tid == 0 && t + kCsrStages < nt) { fence_proxy_async(); issue(t + kCsrStages); }
         }
     } else {
         for (int r = cr0 + tid; r < cr1; r += kDenseThreads) epi(c.row0 + r, 0.0);     // a range of empty rows
@@ -1045,6 +1072,24 @@ __device__ __forceinline__ void dense_body(const DenseCtx& c, const int bid, con
                      [&](int i, double, double p) { c.hook_out[i] = p; });
     } else if constexpr (OP == OP_NORMAL) {
         normal_pass(c.T, k.gtid, k.gstride, k.sm.scratch, [&](int i) { return c.hook_in[i]; }, c.hook_out);
+    } else if constexpr (OP == OP_PROJGRAD) {
+        // projected_gradient(x, g) of the elementwise kinds (solution_spaces.py:162-184, 238-260, 324-347, per leaf of a
+        // DisjointProjOp :527-538): hook_in = x, vec[0] = g, hook_out = normal_vector(x) (an OP_NORMAL launch before this
+        // one); vec[1] = free gradient, vec[2] = chopped gradient.  Box's activity test is the reference's, as written (:339-340).
+        const double *g = c.vec[0], *nv = c.hook_out;
+        double *fr = c.vec[1], *ch = c.vec[2];
+        CCQP_ELEMS(i) {
+            const int kd = c.T.ekind[i];
+            const double x = c.hook_in[i], gi = g[i], lo = c.T.lo[i], hi = c.T.hi[i];
+            bool act = false;
+            if (kd == kLower) act = is_close(x, lo);
+            else if (kd == kUpper) act = is_close(x, hi);
+            else if (kd == kBox) act = is_close(x, hi) || x > hi || is_close(x, (lo != 0.0) ? lo : (x < hi ? 1.0 : 0.0));
+            const double t = nv[i] * gi;
+            const double m = (t < 0.0 || t != t) ? t : 0.0;              // np.min((normal*g, 0)) keeps a NaN
+            fr[i] = act ? 0.0 : gi;
+            ch[i] = act ? gi - m * nv[i] : 0.0;
+        }
     }
 }
 

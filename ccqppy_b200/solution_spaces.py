@@ -7,8 +7,11 @@ arithmetic happens: `op(x)` and `op.normal_vector(x)` run on the GPU through the
 (`ccqp_project` / `ccqp_normal`); inside a solve the operator is never called from Python at all,
 it is handed to the solver kernel as a flat block table (`descriptor()`).
 
-Out of scope, as in SURVEY.md section 2: `plot` and the `projected_gradient` methods (no live
-solver of the reference calls them).
+`projected_gradient(x, g)` (no live solver of the reference calls it) is
+mirrored too, behaviour for behaviour: Lower / Upper / Box / Disjoint run on the GPU
+(`ccqp_projected_gradient`), Identity returns None, Sphere raises NotImplementedError, Cone has no such
+method (only `proximal_gradient`, which raises), a Disjoint with an Identity member raises TypeError.
+Out of scope, as in SURVEY.md section 2: `plot` (presentation code).
 """
 from abc import ABC, abstractmethod
 
@@ -113,6 +116,21 @@ class ProjOpBase(ABC):
         """Outward unit normal at x (zero inside / when x is infeasible), on the GPU."""
         return self._run("ccqp_normal", x)
 
+    def _projected_gradient_gpu(self, x, g):
+        """(free gradient, chopped gradient) through ccqp_projected_gradient; NumPy in, NumPy out."""
+        xin = np.ascontiguousarray(x, dtype=np.float64)
+        gin = np.ascontiguousarray(g, dtype=np.float64)
+        if xin.shape[0] != self.dim or gin.shape[0] != self.dim:
+            raise ValueError("expected vectors of length %d" % self.dim)
+        free, chopped = np.empty_like(xin), np.empty_like(xin)
+        h = _handle()
+        blocks, params, _ = self.descriptor()
+        pp, _, _k1 = _capi.f64_ptr(params if params.size else np.zeros(1))
+        _capi.check(h.h, h.lib.ccqp_set_projection(h.h, blocks.ptr, len(blocks), pp, params.size))
+        P = lambda a: _capi.f64_ptr(a)[0]
+        _capi.check(h.h, h.lib.ccqp_projected_gradient(h.h, P(xin), P(gin), P(free), P(chopped), _capi.MEM_HOST))
+        return free, chopped
+
     def plot(self, *args, **kwargs):
         raise NotImplementedError("plot() is presentation code of the reference and out of scope here")
 
@@ -129,6 +147,10 @@ class IdentityProjOp(ProjOpBase):
 
     def __call__(self, x):
         return x            # the reference returns its argument (alias), :125
+
+    def projected_gradient(self, x, g):
+        """solution_spaces.py:100-109: the reference's method has a docstring and no body, so it returns None."""
+        return None
 
 
 class LowerBoundProjOp(ProjOpBase):
@@ -147,6 +169,10 @@ class LowerBoundProjOp(ProjOpBase):
         params.extend(_per_element(self.lower_bound, self.dim, -1.0))
         return [(_capi.LOWER, offset, self.dim, poff)]
 
+    def projected_gradient(self, x, g):
+        """(free gradient, chopped gradient) at x, solution_spaces.py:162-184, on the GPU."""
+        return self._projected_gradient_gpu(x, g)
+
 
 class UpperBoundProjOp(ProjOpBase):
     """solution_spaces.py:204-277; default bound +1."""
@@ -163,6 +189,10 @@ class UpperBoundProjOp(ProjOpBase):
         poff = len(params)
         params.extend(_per_element(self.upper_bound, self.dim, 1.0))
         return [(_capi.UPPER, offset, self.dim, poff)]
+
+    def projected_gradient(self, x, g):
+        """(free gradient, chopped gradient) at x, solution_spaces.py:238-260, on the GPU."""
+        return self._projected_gradient_gpu(x, g)
 
 
 class BoxProjOp(ProjOpBase):
@@ -183,6 +213,10 @@ class BoxProjOp(ProjOpBase):
         params.extend(_per_element(self.upper_bound, self.dim, 1.0))
         return [(_capi.BOX, offset, self.dim, poff)]
 
+    def projected_gradient(self, x, g):
+        """(free gradient, chopped gradient) at x, solution_spaces.py:324-347 (the activity test of :339-340 as written), on the GPU."""
+        return self._projected_gradient_gpu(x, g)
+
 
 class SphereProjOp(ProjOpBase):
     """solution_spaces.py:369-435; default radius 1."""
@@ -199,6 +233,9 @@ class SphereProjOp(ProjOpBase):
         poff = len(params)
         params.append(float(self.radius))
         return [(_capi.SPHERE, offset, self.dim, poff)]
+
+    def projected_gradient(self, x, g):
+        raise NotImplementedError("Cone proximal gradient not implemented, yet.")     # solution_spaces.py:415, as written
 
 
 class ConeProjOp(ProjOpBase):
@@ -219,6 +256,9 @@ class ConeProjOp(ProjOpBase):
         poff = len(params)
         params.append(float(self.aspect_ratio))
         return [(_capi.CONE_REF, offset, self.dim, poff)]
+
+    def proximal_gradient(self, x, g):
+        raise NotImplementedError("Cone proximal gradient not implemented, yet.")     # solution_spaces.py:467-468
 
 
 class SOCProjOp(ProjOpBase):
@@ -262,6 +302,23 @@ class DisjointProjOp(ProjOpBase):
     @property
     def name(self):
         return "DisjointUnion"
+
+    def projected_gradient(self, x, g):
+        """solution_spaces.py:527-538: every member's projected_gradient on its slice.  Like the reference: a member
+        without the method (Cone) raises AttributeError, Sphere raises NotImplementedError, and an Identity member --
+        whose method returns None -- makes the tuple unpacking raise TypeError.  Otherwise one GPU pass."""
+        def check(members):
+            for op in members:
+                if isinstance(op, DisjointProjOp):
+                    check(op.proj_ops)
+                elif not hasattr(op, "projected_gradient"):
+                    raise AttributeError("'%s' object has no attribute 'projected_gradient'" % type(op).__name__)
+                elif isinstance(op, SphereProjOp):
+                    raise NotImplementedError("Cone proximal gradient not implemented, yet.")
+                elif isinstance(op, IdentityProjOp):
+                    raise TypeError("cannot unpack non-iterable NoneType object")
+        check(self.proj_ops)
+        return self._projected_gradient_gpu(x, g)
 
     def _blocks(self, offset, params):
         rows = []

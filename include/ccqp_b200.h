@@ -193,6 +193,14 @@ ccqp_status ccqp_project(ccqp_handle* h, const double* x, double* out, int memty
 /* out = normal_vector(x): solution_spaces.py:92,146,222,306,389,459,512. */
 ccqp_status ccqp_normal(ccqp_handle* h, const double* x, double* out, int memtype);
 
+/* (free, chopped) = projected_gradient(x, g): solution_spaces.py:162-184 (Lower), :238-260 (Upper), :324-347 (Box, its
+ * activity test as written), :527-538 (Disjoint: leaf by leaf, each with its own leaf's normal_vector).  Elementwise
+ * kinds only: a table with a Sphere / SOC leaf returns CCQP_ERR_UNSUPPORTED (the reference raises NotImplementedError,
+ * :415), one with a reference Cone leaf CCQP_ERR_NORMAL_NOT_IMPLEMENTED; Identity leaves come back as (g, 0) -- the
+ * host mirror reproduces the reference's None / TypeError for them. */
+ccqp_status ccqp_projected_gradient(ccqp_handle* h, const double* x, const double* g, double* free_out,
+                                    double* chopped_out, int memtype);
+
 /* q_k[i] = a_k[i] / b[i], k = 0..2, evaluated with the shared-reciprocal routine the batched SPG kernel uses
  * for its three divisions by d.Ad (solvers.py:954,955,966); must equal IEEE division bit for bit. DEVICE pointers. */
 ccqp_status ccqp_debug_divide(ccqp_handle* h, const double* a0, const double* a1, const double* a2, const double* b,

@@ -154,6 +154,51 @@ def normal_vector(blocks, params, x):
     return out
 
 
+def _projected_gradient_block(kind, par, x, g):
+    """(free gradient, chopped gradient) of one leaf operator, solution_spaces.py:100-109 (Identity: the method has
+    no body and returns None), :162-184 (Lower), :238-260 (Upper), :324-347 (Box, its condition kept as written),
+    :405-415 (Sphere: raises).  ConeProjOp has no such method at all (:467 is `proximal_gradient`)."""
+    d = x.shape[0]
+    if kind == IDENTITY:
+        return None
+    if kind == SPHERE:
+        raise NotImplementedError("Cone proximal gradient not implemented, yet.")      # :415, message as written
+    if kind in (CONE_REF, SOC):
+        raise AttributeError("'ConeProjOp' object has no attribute 'projected_gradient'")
+    nv = _normal_block(kind, par, x)
+    if kind == LOWER:
+        act = np.isclose(x, par[:d])
+    elif kind == UPPER:
+        act = np.isclose(x, par[:d])
+    else:
+        lb, ub = par[:d], par[d:2 * d]
+        # `np.isclose(x[i], self.lower_bound[i] or x[i]<self.upper_bound[i])` (:340): Python's `or` yields the lower
+        # bound unless it is zero (NaN is truthy), else the boolean x[i] < ub[i], which isclose reads as 1.0 / 0.0
+        other = np.where((lb != 0) | np.isnan(lb), lb, (x < ub).astype(float))
+        act = np.isclose(x, ub) | (x > ub) | np.isclose(x, other)
+    t = nv * g
+    chop = g - np.where(np.isnan(t) | (t < 0), t, 0.0) * nv      # g[i] - np.min((normal[i]*g[i], 0))*normal[i]
+    return np.where(act, 0.0, g), np.where(act, chop, 0.0)
+
+
+def projected_gradient(blocks, params, x, g):
+    """projected_gradient(x, g) of the whole table: a single block behaves like the bare operator, several like
+    DisjointProjOp.projected_gradient (solution_spaces.py:527-538), which unpacks every leaf's result -- so an
+    Identity leaf (whose method returns None) makes it raise TypeError, as in the reference."""
+    x, g = np.asarray(x, dtype=np.float64), np.asarray(g, dtype=np.float64)
+    if len(blocks) == 1:
+        kind, off, dim, poff = (int(v) for v in blocks[0])
+        return _projected_gradient_block(kind, params[poff:], x[off:off + dim], g[off:off + dim])
+    free, chop = np.zeros(x.shape[0]), np.zeros(x.shape[0])
+    for kind, off, dim, poff in blocks:
+        kind, off, dim, poff = int(kind), int(off), int(dim), int(poff)
+        r = _projected_gradient_block(kind, params[poff:], x[off:off + dim], g[off:off + dim])
+        if r is None:
+            raise TypeError("cannot unpack non-iterable NoneType object")
+        free[off:off + dim], chop[off:off + dim] = r
+    return free, chop
+
+
 # --------------------------------------------------------------------------------------------
 # solvers                                                               solvers.py:71-1224
 # --------------------------------------------------------------------------------------------

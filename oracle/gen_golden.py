@@ -301,8 +301,62 @@ def gen_projections():
     np.savez_compressed(os.path.join(GOLD, "projections.npz"), **out)
 
 
+def gen_projected_gradients():
+    """projected_gradient(x, g) of the reference (solution_spaces.py:162-184, 238-260, 324-347, 527-538) on seeded
+    points incl. points on the bounds, for the operator kinds that implement it, plus the exceptions of the others."""
+    rng = np.random.default_rng(77)
+    out, errors = {}, {}
+    lb0 = np.where(rng.random(40) < 0.4, 0.0, -1.0 - rng.random(40))          # zero lower bounds hit the `or` branch of :340
+    tabs = {"box": pr.box_table(64), "box_zero_lb": pr.Table().add(pr.BOX, 40, lb0, lb0 + 1.0 + rng.random(40)),
+            "lower": pr.lower_table(33), "upper": pr.upper_table(33),
+            "disjoint": pr.Table().add(pr.BOX, 20, -1.0, 1.0).add(pr.LOWER, 10, -0.5).add(pr.UPPER, 10, 0.25).add(pr.BOX, 7, 0.0, 2.0)}
+    for name, tab in tabs.items():
+        op = ref_op_from_table(tab)
+        n = tab.n
+        X, G, F, C = [], [], [], []
+        for trial in range(24):
+            x = [0.3, 1.0, 1.0, 3.0][trial % 4] * rng.standard_normal(n)
+            if trial % 3 != 0:                         # feasible points with entries exactly on / next to the bounds
+                x = np.asarray(op(x), dtype=float)
+                if trial % 3 == 2:
+                    x = x * (1.0 + 1e-7 * (trial % 5 - 2))
+            if trial % 8 == 1:
+                x[::5] = [0.0, 1.0][trial % 2]         # the values the quirk of :340 compares with
+            g = rng.standard_normal(n)
+            f, c = op.projected_gradient(x, g)
+            of, oc = orc.projected_gradient(tab.blocks, tab.params, x, g)
+            if not (np.array_equal(np.asarray(f, float), of) and np.array_equal(np.asarray(c, float), oc)):
+                raise SystemExit("oracle projected_gradient != reference for %s" % name)
+            X.append(x); G.append(g); F.append(np.asarray(f, float)); C.append(np.asarray(c, float))
+        out[name + "/x"], out[name + "/g"], out[name + "/free"], out[name + "/chopped"] = map(np.array, (X, G, F, C))
+        print("projected_gradient %-12s ok (%d points, n=%d)" % (name, len(X), n))
+    for name, tab in {"identity": pr.identity_table(5), "sphere": pr.sphere_table(5), "cone": pr.cone_ref_table(5),
+                      "disjoint_with_identity": pr.Table().add(pr.BOX, 3, -1.0, 1.0).add(pr.IDENTITY, 2)}.items():
+        op = ref_op_from_table(tab)
+        x, g = rng.standard_normal(5), rng.standard_normal(5)
+        def outcome(fn):
+            try:
+                r = fn()
+                return "None" if r is None else "value"
+            except Exception as e:      # noqa: BLE001
+                return type(e).__name__
+        ref = outcome(lambda: op.projected_gradient(x, g))
+        mine = outcome(lambda: orc.projected_gradient(tab.blocks, tab.params, x, g))
+        if ref != mine:
+            raise SystemExit("oracle projected_gradient behaviour != reference for %s: %s vs %s" % (name, mine, ref))
+        errors[name] = ref
+    np.savez_compressed(os.path.join(GOLD, "projected_gradients.npz"), **out)
+    with open(os.path.join(GOLD, "projected_gradients.json"), "w") as f:
+        json.dump(errors, f, indent=0)
+    print("projected_gradient behaviours:", errors)
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
+    if "--projected-gradients-only" in sys.argv:
+        gen_projected_gradients()
+        sys.exit(0)
     gen_projections()
+    gen_projected_gradients()
     gen_solvers()
     print("numpy", np.__version__)

@@ -354,3 +354,42 @@ def test_benchmark_driver_with_the_gpu_generator():
     small = benchmark.BenchmarkRandomCCQP(1, [], [[ss.BoxProjOp(6)]])
     As, _ = small.generate_random_convex_quadratic_func(6, 0)
     assert isinstance(As, np.ndarray)
+
+
+def test_projected_gradient_matches_reference_goldens_and_behaviours():
+    """Row f-4: `op.projected_gradient(x, g)` on the GPU (ccqp_projected_gradient) against the goldens generated from the
+    live reference (solution_spaces.py:162-184, 238-260, 324-347, 527-538): bit for bit; and the reference's behaviour for
+    the operators that do not implement it (Identity -> None, Sphere -> NotImplementedError, Cone -> AttributeError,
+    Disjoint with an Identity member -> TypeError)."""
+    from test_oracle_golden import PG, PG_TABLES, PG_BEHAVIOUR
+    from ccqppy_b200 import solution_spaces as ss
+    for name, tab in PG_TABLES.items():
+        op = op_from_table(tab)
+        for x, g, f, c in zip(PG[name + "/x"], PG[name + "/g"], PG[name + "/free"], PG[name + "/chopped"]):
+            gf, gc = op.projected_gradient(x, g)
+            assert np.array_equal(gf, f) and np.array_equal(gc, c), name
+    x, g = np.linspace(-1, 1, 5), np.linspace(2, -2, 5)
+    ops = {"identity": ss.IdentityProjOp(5), "sphere": ss.SphereProjOp(5), "cone": ss.ConeProjOp(5),
+           "disjoint_with_identity": ss.DisjointProjOp(ss.BoxProjOp(3), ss.IdentityProjOp(2))}
+    for name, op in ops.items():
+        try:
+            r = op.projected_gradient(x, g)
+            got = "None" if r is None else "value"
+        except Exception as e:      # noqa: BLE001
+            got = type(e).__name__
+        assert got == PG_BEHAVIOUR[name], name
+    with pytest.raises(NotImplementedError):
+        ss.ConeProjOp(5).proximal_gradient(x, g)
+    with pytest.raises(NotImplementedError):
+        ss.DisjointProjOp(ss.BoxProjOp(2), ss.SphereProjOp(3)).projected_gradient(x, g)
+    # large vector, NaN gradient entries propagate like np.min((nan, 0))
+    n = 5000
+    rng = np.random.default_rng(3)
+    op = ss.BoxProjOp(n)
+    xb = np.clip(2 * rng.standard_normal(n), -1, 1)
+    gb = rng.standard_normal(n)
+    gb[::97] = np.nan
+    tab = pr.box_table(n)
+    of, oc = orc.projected_gradient(tab.blocks, tab.params, xb, gb)
+    gf, gc = op.projected_gradient(xb, gb)
+    assert np.array_equal(gf, of, equal_nan=True) and np.array_equal(gc, oc, equal_nan=True)

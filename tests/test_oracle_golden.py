@@ -117,3 +117,40 @@ def test_cone_normal_raises_like_reference():
 def test_readme_counts():
     got = {c["name"]: c["mv"] for c in META if c["name"].startswith("readme/")}
     assert got == {"readme/SPG/seed0": 92, "readme/SPG/seed1": 89, "readme/SPG/seed2": 93}
+
+
+PG = np.load(os.path.join(GOLD, "projected_gradients.npz"))
+PG_BEHAVIOUR = json.load(open(os.path.join(GOLD, "projected_gradients.json")))
+_lb0_rng = np.random.default_rng(77)      # gen_golden.gen_projected_gradients draws the zero-lower-bound table first
+
+
+def projected_gradient_tables():
+    lb0 = np.where(_lb0_rng.random(40) < 0.4, 0.0, -1.0 - _lb0_rng.random(40))
+    return {"box": pr.box_table(64), "box_zero_lb": pr.Table().add(pr.BOX, 40, lb0, lb0 + 1.0 + _lb0_rng.random(40)),
+            "lower": pr.lower_table(33), "upper": pr.upper_table(33),
+            "disjoint": pr.Table().add(pr.BOX, 20, -1.0, 1.0).add(pr.LOWER, 10, -0.5).add(pr.UPPER, 10, 0.25).add(pr.BOX, 7, 0.0, 2.0)}
+
+
+PG_TABLES = projected_gradient_tables()
+
+
+@pytest.mark.parametrize("name", sorted(PG_TABLES))
+def test_oracle_projected_gradient_matches_reference_goldens(name):
+    """Row f-4: projected_gradient(x, g) (solution_spaces.py:162-184, 238-260, 324-347, 527-538), bit for bit."""
+    tab = PG_TABLES[name]
+    for x, g, f, c in zip(PG[name + "/x"], PG[name + "/g"], PG[name + "/free"], PG[name + "/chopped"]):
+        of, oc = orc.projected_gradient(tab.blocks, tab.params, x, g)
+        assert np.array_equal(of, f) and np.array_equal(oc, c)
+
+
+def test_oracle_projected_gradient_exceptions_match_reference():
+    x, g = np.linspace(-1, 1, 5), np.linspace(2, -2, 5)
+    tabs = {"identity": pr.identity_table(5), "sphere": pr.sphere_table(5), "cone": pr.cone_ref_table(5),
+            "disjoint_with_identity": pr.Table().add(pr.BOX, 3, -1.0, 1.0).add(pr.IDENTITY, 2)}
+    for name, tab in tabs.items():
+        try:
+            r = orc.projected_gradient(tab.blocks, tab.params, x, g)
+            got = "None" if r is None else "value"
+        except Exception as e:      # noqa: BLE001
+            got = type(e).__name__
+        assert got == PG_BEHAVIOUR[name], name

@@ -107,6 +107,34 @@ def test_projections_and_normals_bit_for_bit(seed, n, scale):
             assert np.array_equal(orc.normal_vector(tab.blocks, tab.params, x.copy()), np.asarray(op.normal_vector(x.copy()), dtype=float))
 
 
+@settings(max_examples=60, deadline=None)
+@given(seed=st.integers(0, 2 ** 31 - 1), n=st.integers(1, 30), kind=st.sampled_from(["lower", "upper", "box", "box0", "disjoint"]),
+       on_boundary=st.booleans())
+def test_projected_gradient_bit_for_bit(seed, n, kind, on_boundary):
+    """Row f-4: solution_spaces.py:162-184, 238-260, 324-347 (incl. the `lower_bound[i] or ...` test of :340), 527-538."""
+    rng = np.random.default_rng(seed)
+    lo = np.where(rng.random(n) < 0.3, 0.0, -rng.random(n) - 0.2) if kind == "box0" else -rng.random(n) - 0.2
+    hi = lo + 0.5 + rng.random(n)
+    tab = pr.Table()
+    if kind == "lower":
+        tab.add(pr.LOWER, n, lo)
+    elif kind == "upper":
+        tab.add(pr.UPPER, n, hi)
+    elif kind in ("box", "box0"):
+        tab.add(pr.BOX, n, lo, hi)
+    else:
+        tab.add(pr.BOX, n, lo, hi).add(pr.LOWER, n, lo).add(pr.UPPER, n, hi)
+    op = ref_op(tab)
+    x = 1.5 * rng.standard_normal(tab.n)
+    if on_boundary:
+        x = np.asarray(op(x), dtype=float)
+        x[rng.random(tab.n) < 0.2] = [0.0, 1.0][seed % 2]
+    g = rng.standard_normal(tab.n)
+    f, c = op.projected_gradient(x, g)
+    of, oc = orc.projected_gradient(tab.blocks, tab.params, x, g)
+    assert np.array_equal(np.asarray(f, float), of) and np.array_equal(np.asarray(c, float), oc)
+
+
 @settings(max_examples=25, deadline=None)
 @given(seed=st.integers(0, 2 ** 31 - 1), n=st.integers(2, 48), solver=st.sampled_from(list(range(7))),
        mu=st.sampled_from([1.0, 0.1]), warm=st.booleans())
