@@ -41,7 +41,7 @@
 #include <string>
 #include <vector>
 
-#include "common.cuh"
+#include "proj.cuh"
 #include "../../include/ccqp_b200.h"
 
 #ifndef CCQP_BATCHED_STAGE
@@ -74,8 +74,16 @@ struct BatchedCtx {
     const double* A;        // [batch][n][n]
     const double* b;        // [batch][n]
     const double* x0;       // [batch][n] or null
-    const double* lb;
+    const double* lb;       // [batch][n]; general table: [n], shared by all problems (bound_stride = 0)
     const double* ub;
+    long long bound_stride; // n (per-problem bounds) or 0
+    // general projection table shared by all problems of the batch (ccqp_solve_batched_table); null = Box per problem
+    const uint8_t* ekind;   // [n] kIdentity / kLower / kUpper / kBox / kElemNorm
+    const int* eoff;        // [n] first element of the norm block the element belongs to
+    const int* edim;        // [n] its dimension
+    const int* enk;         // [n] its kind (kSphere / kConeRef / kSoc)
+    const double* epar;     // [n] its parameter (radius / aspect ratio)
+    int has_norm;           // some element belongs to a norm block
     const double* uniforms; // [batch][n_uniforms]
     long long n_uniforms;
     double* x_out;          // [batch][n]
@@ -99,6 +107,7 @@ struct BatchedSmem {
 #endif
     double xs[2][kBXs];     // mat-vec input, double buffered; slices padded by 16 bytes (16-byte aligned)
     double red[2][2][4];    // [parity][warp][slot]
+    double pj[2][kBN];      // general table: the vector being projected, for the members of norm blocks
 #if CCQP_BATCHED_STAGE
     uint64_t mbar;
 #endif
@@ -251,7 +260,41 @@ struct BState {                 // per-thread view of one problem (thread t <-> 
     double b, lo, hi, x0;
     double cs;                  // 1/(3 n gd)
     bool act;                   // t < n
+    // general table only
+    int kind;                   // element kind
+    int boff, bdim, bnk;        // norm block of this element
+    double bpar;
+    uint32_t pj;                // shared address of pj[0][0]
 };
+
+// P(t)_own for the general table.  Elementwise kinds: compare/select as in proj.cuh.  Members of a norm block (Sphere /
+// reference Cone / SOC of any dimension <= n): the vector goes through shared memory, every member reads its block and
+// forms the norm with the sequential FMA chain of project_pass (proj.cuh), then applies the block's rule to its own entry.
+// Every thread of the CTA must call it (one barrier when the table has norm blocks).
+__device__ __forceinline__ double project_general(const BState& s, bool has_norm, int& ppar, double t) {
+    double p = clamp_elem(s.kind, t, s.lo, s.hi);
+    if (has_norm) {
+        const uint32_t base = s.pj + (uint32_t)ppar * (kBN * 8u);
+        sts_f64(base + threadIdx.x * 8u, t);
+        __syncthreads();
+        if (s.kind == kElemNorm) {
+            NormRule R;
+            R.kind = s.bnk; R.par = s.bpar;
+            const int nsq = (s.bnk == kSoc) ? s.bdim - 1 : s.bdim;
+            double ss = 0.0, last = 0.0;
+            for (int j = 0; j < s.bdim; ++j) {
+                const double tj = lds_f64(base + (uint32_t)(s.boff + j) * 8u);
+                if (j < nsq) ss = (j == 0) ? tj * tj : fma(tj, tj, ss);
+                last = tj;
+            }
+            R.r = sqrt(ss); R.last = last;
+            R.finish();
+            p = R.apply(t, (int)threadIdx.x == s.boff + s.bdim - 1);
+        }
+        ppar ^= 1;
+    }
+    return p;
+}
 
 // SPG's deque(maxlen=m) (solvers.py:931).  Only max() over the contents is ever taken (:953), so the
 // order of the entries is irrelevant: for the reference default m = 5 the window is a 5-register
@@ -292,14 +335,17 @@ struct SpgWindow {
     }
 };
 
-template <int SOLVER, bool WREG>
+template <int SOLVER, bool WREG, bool GEN>
 __device__ __forceinline__ void solve_one(const BatchedCtx& c, const double (&a)[kBRows][kBCols], const BShared& sm,
                                           const BState& s, const double* uni, int& par, int& xpar, double& xsol,
                                           BatchedOut& o) {
     int mv = 0, gemv = 0, iters = 0, draws = 0, status = 0;
     double res = NAN;
     const int maxmv = c.max_mv_i;
-    auto resid2 = [&](double x, double g) { const double d = s.cs * (x - clampd(x - kGd * g, s.lo, s.hi)); return d * d; };
+    int ppar = 0;
+    // the projection: Box per problem (solution_spaces.py:363-366), or the batch's general table
+    auto P = [&](double t) { if constexpr (GEN) return project_general(s, c.has_norm != 0, ppar, t); else return clampd(t, s.lo, s.hi); };
+    auto resid2 = [&](double x, double g) { const double d = s.cs * (x - P(x - kGd * g)); return d * d; };
 
     if constexpr (SOLVER == CCQP_SOLVER_PGD || SOLVER == CCQP_SOLVER_BBPGD || SOLVER == CCQP_SOLVER_BBPGDF) {
         // solvers.py:114-170, 606-669, 741-819
@@ -317,7 +363,7 @@ __device__ __forceinline__ void solve_one(const BatchedCtx& c, const double (&a)
                 step = q[0] / q[1];
             }
             for (;;) {
-                x = clampd(xm - step * gm, s.lo, s.hi);
+                x = P(xm - step * gm);
                 g = matvec(a, sm, xpar, s.act, x) + s.b; gemv++; mv++;
                 if (mv >= maxmv) break;
                 const double sx = x - xm, sy = g - gm;
@@ -331,7 +377,7 @@ __device__ __forceinline__ void solve_one(const BatchedCtx& c, const double (&a)
                     res = sqrt(res2);
                     if (res < resmin) { resmin = res; xmin = x; gmin = g; }
                     if (step < 10 * kEps) {
-                        x = clampd(xmin - kGd * gmin, s.lo, s.hi);
+                        x = P(xmin - kGd * gmin);
                         const double sx2 = x - xm;
                         double q2[2] = {sx2 * sx2, sx2 * sy};
                         cta64_sum<2>(q2, sm, par);
@@ -358,7 +404,7 @@ __device__ __forceinline__ void solve_one(const BatchedCtx& c, const double (&a)
         win.init(f);
         double dd_rep = NAN;
         for (;;) {
-            const double d = clampd(x - alpha * g, s.lo, s.hi) - x;
+            const double d = P(x - alpha * g) - x;
             const double ad = matvec(a, sm, xpar, s.act, d); gemv++; mv++;
             if (mv >= maxmv) break;
             double q[3] = {d * d, d * ad, d * g};
@@ -398,7 +444,7 @@ __device__ __forceinline__ void solve_one(const BatchedCtx& c, const double (&a)
             const double ay = matvec(a, sm, xpar, s.act, y); gemv++; mv++;
             if (mv >= maxmv) break;
             const double g = ay + s.b;
-            xp = clampd(y - t * g, s.lo, s.hi);
+            xp = P(y - t * g);
             bool have12 = false;
             double rt1 = 0.0, rt2 = 0.0;
             for (;;) {
@@ -417,7 +463,7 @@ __device__ __forceinline__ void solve_one(const BatchedCtx& c, const double (&a)
                 if ((qa[0] * 0.5 + qa[1]) <= (rt1 + rt2 + qa[2] + 0.5 * L * qa[3])) break;
                 L *= 2;
                 t = 1.0 / L;
-                xp = clampd(y - t * g, s.lo, s.hi);
+                xp = P(y - t * g);
             }
             double theta_n = 0.5 * (-theta * theta + theta * sqrt(4 + theta * theta));
             const double beta = theta * (1 - theta) / (theta * theta + theta_n);
@@ -555,8 +601,8 @@ constexpr int batched_min_ctas(int solver) {
     return (solver == CCQP_SOLVER_PGD || solver == CCQP_SOLVER_BBPGD || solver == CCQP_SOLVER_SPG) ? CCQP_BATCHED_CTAS : 5;
 }
 
-template <int SOLVER, bool WREG>
-__global__ void __launch_bounds__(kBN, batched_min_ctas(SOLVER)) batched_kernel(const BatchedCtx c) {
+template <int SOLVER, bool WREG, bool GEN>
+__global__ void __launch_bounds__(kBN, GEN ? 5 : batched_min_ctas(SOLVER)) batched_kernel(const BatchedCtx c) {
     __shared__ __align__(16) BatchedSmem sm;
     const int t = threadIdx.x, n = c.n;
     const int cb = t & (kBRows - 1), row0 = kBRows * (t >> kBLog), col0 = kBCols * cb;
@@ -633,9 +679,16 @@ __global__ void __launch_bounds__(kBN, batched_min_ctas(SOLVER)) batched_kernel(
         BState s;
         s.act = t < n;
         const size_t vo = (size_t)cur * n + t;
+        const size_t bo = (size_t)cur * c.bound_stride + t;
         s.b = s.act ? c.b[vo] : 0.0;
-        s.lo = s.act ? c.lb[vo] : 0.0;
-        s.hi = s.act ? c.ub[vo] : 0.0;
+        s.lo = s.act ? c.lb[bo] : 0.0;
+        s.hi = s.act ? c.ub[bo] : 0.0;
+        if constexpr (GEN) {
+            s.kind = s.act ? c.ekind[t] : kIdentity;
+            s.boff = s.act ? c.eoff[t] : 0; s.bdim = s.act ? c.edim[t] : 0; s.bnk = s.act ? c.enk[t] : 0;
+            s.bpar = s.act ? c.epar[t] : 0.0;
+            s.pj = smem_u32(&sm.pj[0][0]);
+        }
         s.x0 = (s.act && c.x0) ? c.x0[vo] : 0.0;
         s.cs = 1.0 / (3 * (double)n * kGd);
         __syncthreads();
@@ -649,8 +702,8 @@ __global__ void __launch_bounds__(kBN, batched_min_ctas(SOLVER)) batched_kernel(
 
         double xsol = 0.0;
         BatchedOut o;
-        solve_one<SOLVER, WREG>(c, a, sh, s, c.uniforms ? c.uniforms + (size_t)cur * c.n_uniforms : nullptr, par, xpar,
-                                xsol, o);
+        solve_one<SOLVER, WREG, GEN>(c, a, sh, s, c.uniforms ? c.uniforms + (size_t)cur * c.n_uniforms : nullptr, par, xpar,
+                                     xsol, o);
         if (s.act) c.x_out[vo] = xsol;
         if (t == 0) c.out[cur] = o;
         cur = nxt;
@@ -687,22 +740,31 @@ inline double sqrt_threshold(double tol, bool strict) {
     return out;
 }
 
-template <int SOLVER, bool WREG>
+template <int SOLVER, bool WREG, bool GEN = false>
 inline cudaError_t launch_batched(const BatchedCtx& c, int sm_count, cudaStream_t stream) {
     int per_sm = 0;
-    cudaFuncSetAttribute(batched_kernel<SOLVER, WREG>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, batched_kernel<SOLVER, WREG>, kBN, 0);
+    cudaFuncSetAttribute(batched_kernel<SOLVER, WREG, GEN>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, batched_kernel<SOLVER, WREG, GEN>, kBN, 0);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     if (const char* e = getenv("CCQP_BATCHED_CTAS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(e)));   // tuning hook
     long long grid = (long long)sm_count * per_sm;
     if (grid > c.batch) grid = c.batch;
-    batched_kernel<SOLVER, WREG><<<(unsigned)grid, kBN, 0, stream>>>(c);
+    batched_kernel<SOLVER, WREG, GEN><<<(unsigned)grid, kBN, 0, stream>>>(c);
     return cudaGetLastError();
 }
 
+// One projection table shared by every problem of a batch (ccqp_solve_batched_table), per element, on the HOST
+struct BatchedTable {
+    std::vector<double> lo, hi, epar;
+    std::vector<uint8_t> ekind;
+    std::vector<int> eoff, edim, enk;
+    int has_norm = 0;
+};
+
 // Returns a ccqp_status.  `alloc(bytes)` returns a device workspace of at least that size.
-inline int batched_solve(cudaStream_t stream, int sm_count, void*, size_t, int solver, const ccqp_params& prm,
+// tab != nullptr: the general table replaces the per-problem Box (lb / ub are ignored).
+inline int batched_solve(cudaStream_t stream, int sm_count, const BatchedTable* tab, size_t, int solver, const ccqp_params& prm,
                          long long batch, long long n, const double* A, const double* b, const double* x0,
                          const double* lb, const double* ub, const double* uniforms, long long n_uniforms, double* x_out,
                          int memtype, ccqp_result* results, ccqp_result* summary, cudaEvent_t ev0, cudaEvent_t ev1,
@@ -710,6 +772,7 @@ inline int batched_solve(cudaStream_t stream, int sm_count, void*, size_t, int s
 #define BCU(call)                                                                                  \
     do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { err = std::string(#call) + ": " + cudaGetErrorString(e__); return CCQP_ERR_CUDA; } } while (0)
     if (n > kBN) return CCQP_ERR_UNSUPPORTED;
+    if (tab && solver == CCQP_SOLVER_MPRGP) return CCQP_ERR_UNSUPPORTED;     // batched MPRGP: Box per problem only
     if (batch >= (1LL << 31) - 1024) return CCQP_ERR_INVALID_ARG;
     const bool host = memtype == CCQP_MEM_HOST;
     if (solver == CCQP_SOLVER_SPG && (n_uniforms < 0 || (n_uniforms > 0 && !uniforms))) return CCQP_ERR_INVALID_ARG;
@@ -717,7 +780,7 @@ inline int batched_solve(cudaStream_t stream, int sm_count, void*, size_t, int s
     const size_t szU = (solver == CCQP_SOLVER_SPG) ? (size_t)batch * n_uniforms * 8 : 0;
     const size_t szO = (size_t)batch * sizeof(BatchedOut);
     auto al = [](size_t v) { return (v + 255) / 256 * 256; };
-    size_t total = 256 + al(szO);
+    size_t total = 256 + al(szO) + 8 * al((size_t)kBN * 8);
     if (host) total += al(szA) + 4 * al(szV) + al(szV) + al(szU);
     unsigned char* ws = static_cast<unsigned char*>(alloc(total));
     if (!ws) { err = "workspace allocation failed"; return CCQP_ERR_CUDA; }
@@ -737,14 +800,31 @@ inline int batched_solve(cudaStream_t stream, int sm_count, void*, size_t, int s
         double* du = szU ? reinterpret_cast<double*>(take(szU)) : nullptr;
         BCU(cudaMemcpyAsync(dA, A, szA, cudaMemcpyHostToDevice, stream));
         BCU(cudaMemcpyAsync(db, b, szV, cudaMemcpyHostToDevice, stream));
-        BCU(cudaMemcpyAsync(dlb, lb, szV, cudaMemcpyHostToDevice, stream));
-        BCU(cudaMemcpyAsync(dub, ub, szV, cudaMemcpyHostToDevice, stream));
+        if (!tab) BCU(cudaMemcpyAsync(dlb, lb, szV, cudaMemcpyHostToDevice, stream));
+        if (!tab) BCU(cudaMemcpyAsync(dub, ub, szV, cudaMemcpyHostToDevice, stream));
         if (x0) BCU(cudaMemcpyAsync(dx0, x0, szV, cudaMemcpyHostToDevice, stream));
         if (du) BCU(cudaMemcpyAsync(du, uniforms, szU, cudaMemcpyHostToDevice, stream));
         c.A = dA; c.b = db; c.lb = dlb; c.ub = dub; c.x0 = x0 ? dx0 : nullptr; c.uniforms = du; c.x_out = dxo;
     } else {
         c.A = A; c.b = b; c.lb = lb; c.ub = ub; c.x0 = x0; c.uniforms = (solver == CCQP_SOLVER_SPG) ? uniforms : nullptr;
         c.x_out = x_out;
+    }
+    c.bound_stride = n;
+    if (tab) {        // the shared table: seven small per-element arrays, uploaded once per call
+        auto up = [&](const void* src, size_t bytes) -> void* {
+            void* d = take((size_t)kBN * 8);
+            return cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, stream) == cudaSuccess ? d : nullptr;
+        };
+        c.lb = static_cast<const double*>(up(tab->lo.data(), (size_t)n * 8));
+        c.ub = static_cast<const double*>(up(tab->hi.data(), (size_t)n * 8));
+        c.epar = static_cast<const double*>(up(tab->epar.data(), (size_t)n * 8));
+        c.ekind = static_cast<const uint8_t*>(up(tab->ekind.data(), (size_t)n));
+        c.eoff = static_cast<const int*>(up(tab->eoff.data(), (size_t)n * 4));
+        c.edim = static_cast<const int*>(up(tab->edim.data(), (size_t)n * 4));
+        c.enk = static_cast<const int*>(up(tab->enk.data(), (size_t)n * 4));
+        if (!c.lb || !c.ub || !c.epar || !c.ekind || !c.eoff || !c.edim || !c.enk) { err = "table upload failed"; return CCQP_ERR_CUDA; }
+        c.has_norm = tab->has_norm;
+        c.bound_stride = 0;
     }
     c.n_uniforms = (solver == CCQP_SOLVER_SPG) ? n_uniforms : 0;
     c.out = dout; c.counter = counter;
@@ -762,7 +842,19 @@ inline int batched_solve(cudaStream_t stream, int sm_count, void*, size_t, int s
     BCU(cudaEventRecord(ev0, stream));
     cudaError_t le;
     const bool wreg = prm.m == kBWinReg;
-    switch (solver) {
+    if (tab) switch (solver) {
+        case CCQP_SOLVER_PGD: le = launch_batched<CCQP_SOLVER_PGD, true, true>(c, sm_count, stream); break;
+        case CCQP_SOLVER_APGD: le = launch_batched<CCQP_SOLVER_APGD, true, true>(c, sm_count, stream); break;
+        case CCQP_SOLVER_APGD_AR: le = launch_batched<CCQP_SOLVER_APGD_AR, true, true>(c, sm_count, stream); break;
+        case CCQP_SOLVER_BBPGD: le = launch_batched<CCQP_SOLVER_BBPGD, true, true>(c, sm_count, stream); break;
+        case CCQP_SOLVER_BBPGDF: le = launch_batched<CCQP_SOLVER_BBPGDF, true, true>(c, sm_count, stream); break;
+        case CCQP_SOLVER_SPG:
+            le = wreg ? launch_batched<CCQP_SOLVER_SPG, true, true>(c, sm_count, stream)
+                      : launch_batched<CCQP_SOLVER_SPG, false, true>(c, sm_count, stream);
+            break;
+        default: return CCQP_ERR_INVALID_ARG;
+    }
+    else switch (solver) {
         case CCQP_SOLVER_PGD: le = launch_batched<CCQP_SOLVER_PGD, true>(c, sm_count, stream); break;
         case CCQP_SOLVER_APGD: le = launch_batched<CCQP_SOLVER_APGD, true>(c, sm_count, stream); break;
         case CCQP_SOLVER_APGD_AR: le = launch_batched<CCQP_SOLVER_APGD_AR, true>(c, sm_count, stream); break;

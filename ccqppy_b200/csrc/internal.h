@@ -20,6 +20,13 @@ int batched_solve_entry(cudaStream_t stream, int sm_count, int solver, const ccq
                         ccqp_result* summary, cudaEvent_t ev0, cudaEvent_t ev1, int* launches, std::string& err,
                         const std::function<void*(size_t)>& alloc);
 
+// the same with ONE projection table (any block kinds) shared by all problems of the batch instead of a Box per problem
+int batched_solve_table_entry(cudaStream_t stream, int sm_count, int solver, const ccqp_params& prm, long long batch, long long n,
+                              const double* A, const double* b, const double* x0, const ccqp_block* blocks, long long n_blocks,
+                              const double* params, long long n_params, const double* uniforms, long long n_uniforms, double* x_out,
+                              int memtype, ccqp_result* results, ccqp_result* summary, cudaEvent_t ev0, cudaEvent_t ev1, int* launches,
+                              std::string& err, const std::function<void*(size_t)>& alloc);
+
 // emu.cu -- one cooperative launch of dense_kernel_emu<solver> over world * G CTAs
 cudaError_t launch_dense_emu(int solver, const DenseCtx* d_ctxs, int world, int G, size_t smem, cudaStream_t stream);
 

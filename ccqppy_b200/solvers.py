@@ -237,9 +237,13 @@ class CCQPSolverBase(ABC):
         cap = max(256, (1 << 30) // (8 * max(int(batch), 1)))
         return max(1, int(min(mx, cap))) if np.isfinite(mx) else min(cap, 4096)
 
-    def solve_batched(self, A, b, lower_bound, upper_bound, x0=None, seeds=None, uniforms=None, n_uniforms=None,
-                      device=-1):
-        """Extension: solve `batch` independent box-constrained QPs in one persistent kernel.
+    def solve_batched(self, A, b, lower_bound=None, upper_bound=None, x0=None, seeds=None, uniforms=None, n_uniforms=None,
+                      device=-1, convex_proj_op=None):
+        """Extension: solve `batch` independent constrained QPs in one persistent kernel.
+
+        Either per-problem boxes (`lower_bound` / `upper_bound` [batch, n]) or ONE operator of
+        `ccqppy_b200.solution_spaces` shared by all problems (`convex_proj_op`, any block kinds: the
+        contact-style case where every problem has the same friction-disc structure; all solvers except MPRGP).
 
         A [batch, n, n], b / lower_bound / upper_bound / x0 [batch, n] (NumPy or torch, host or
         device).  Problem i equals `type(self)(tol, max_mv).solve(A[i], b[i], x0[i],
@@ -259,8 +263,19 @@ class CCQPSolverBase(ABC):
         A64 = _as_f64(A, dev)
         batch, n = int(A64.shape[0]), int(A64.shape[1])
         b64 = _as_f64(b, dev)
-        lb64 = _as_f64(np.broadcast_to(lower_bound, (batch, n)) if isinstance(lower_bound, np.ndarray) else lower_bound, dev)
-        ub64 = _as_f64(np.broadcast_to(upper_bound, (batch, n)) if isinstance(upper_bound, np.ndarray) else upper_bound, dev)
+        if convex_proj_op is not None:
+            if lower_bound is not None or upper_bound is not None:
+                raise ValueError("give either lower_bound / upper_bound or convex_proj_op")
+            if not isinstance(convex_proj_op, ss.ProjOpBase):
+                raise TypeError("convex_proj_op must be an operator from ccqppy_b200.solution_spaces")
+            if convex_proj_op.embedded_dimension != n:
+                raise ValueError("convex_proj_op has dimension %d, the problems %d" % (convex_proj_op.embedded_dimension, n))
+            lb64 = ub64 = None
+        else:
+            if lower_bound is None or upper_bound is None:
+                raise ValueError("lower_bound and upper_bound (or convex_proj_op) are required")
+            lb64 = _as_f64(np.broadcast_to(lower_bound, (batch, n)) if isinstance(lower_bound, np.ndarray) else lower_bound, dev)
+            ub64 = _as_f64(np.broadcast_to(upper_bound, (batch, n)) if isinstance(upper_bound, np.ndarray) else upper_bound, dev)
         x064 = None if x0 is None else _as_f64(x0, dev)
         uni = None
         K = 0
@@ -289,9 +304,16 @@ class CCQPSolverBase(ABC):
         results = (_capi.Result * batch)()
         summary = _capi.Result()
         prm = self._params()
-        st = lib.ccqp_solve_batched(h.h, self._solver_id, ctypes.byref(prm), batch, n, ptrs[0][0], ptrs[1][0],
-                                    ptrs[2][0], ptrs[3][0], ptrs[4][0], ptrs[5][0], K, ptrs[6][0], mem, results,
-                                    ctypes.byref(summary))
+        if convex_proj_op is not None:
+            blocks, params, _rows = convex_proj_op.descriptor()
+            pp, _, _kp = _capi.f64_ptr(params if params.size else np.zeros(1))
+            st = lib.ccqp_solve_batched_table(h.h, self._solver_id, ctypes.byref(prm), batch, n, ptrs[0][0], ptrs[1][0],
+                                              ptrs[2][0], blocks.ptr, len(blocks), pp, params.size, ptrs[5][0], K,
+                                              ptrs[6][0], mem, results, ctypes.byref(summary))
+        else:
+            st = lib.ccqp_solve_batched(h.h, self._solver_id, ctypes.byref(prm), batch, n, ptrs[0][0], ptrs[1][0],
+                                        ptrs[2][0], ptrs[3][0], ptrs[4][0], ptrs[5][0], K, ptrs[6][0], mem, results,
+                                        ctypes.byref(summary))
         _capi.check(h.h, st)
         rec = np.frombuffer(results, dtype=np.dtype([("residual", "f8"), ("gpu_seconds", "f8"), ("hbm_bytes", "f8"),
                                                      ("mv", "i8"), ("gemv", "i8"), ("it", "i8"), ("draws", "i8"),

@@ -182,6 +182,17 @@ ccqp_status ccqp_solve_batched(ccqp_handle* h, int solver, const ccqp_params* pa
                                int64_t n_uniforms, double* x_out, int memtype,
                                ccqp_result* results, ccqp_result* summary);
 
+/* The same with ONE feasible set shared by all problems of the batch, given as a block table (any block kinds:
+ * DisjointProjOp of Box / Lower / Upper / Identity / Sphere / reference Cone / SOC leaves, solution_spaces.py:77-560) --
+ * the contact-style case: every problem has the same friction-disc structure.  Problem i equals
+ *     CCQPSolverX(tol,max_mv).solve(A[i], b[i], x0[i], op)        with op described by blocks / block_params
+ * (host pointers, as for ccqp_set_projection).  All solvers except MPRGP (CCQP_ERR_UNSUPPORTED). */
+ccqp_status ccqp_solve_batched_table(ccqp_handle* h, int solver, const ccqp_params* params, int64_t batch,
+                                     int64_t n, const double* A, const double* b, const double* x0,
+                                     const ccqp_block* blocks, int64_t n_blocks, const double* block_params,
+                                     int64_t n_params, const double* uniforms, int64_t n_uniforms, double* x_out,
+                                     int memtype, ccqp_result* results, ccqp_result* summary);
+
 /* ---- unit-test hooks for the pieces of the path ---------------------------------------------- */
 /* y = A v for the handle's row shard (y has n_rows entries).  A.dot(v), solvers.py:133 etc. */
 ccqp_status ccqp_gemv(ccqp_handle* h, const double* v, double* y, int memtype);

@@ -127,3 +127,76 @@ def test_batched_spg_hyperparameters(m, tau, sig1, sig2):
             same += 1
             assert np.linalg.norm(s.solution[i] - o["solution"]) <= 1e-9 * np.linalg.norm(o["solution"])
     assert same >= 0.9 * batch
+
+
+def small_mixed_table(n, seed=5):
+    """Disjoint(Box, Lower, Upper, k x Sphere(3), Sphere(2), Identity) on n >= 24 unknowns."""
+    rng = np.random.default_rng(seed)
+    nb, nl, nu = n // 4, n // 8, n // 8
+    t = pr.Table()
+    lo = -1.0 - 0.5 * rng.random(nb)
+    t.add(pr.BOX, nb, lo, lo + 1.5 + rng.random(nb))
+    t.add(pr.LOWER, nl, -0.5 - rng.random(nl))
+    t.add(pr.UPPER, nu, 0.5 + rng.random(nu))
+    while t.n + 3 <= n - 3:
+        t.add(pr.SPHERE, 3, 0.3 + rng.random())
+    t.add(pr.SPHERE, 2, 0.7)
+    if t.n < n:
+        t.add(pr.IDENTITY, n - t.n)
+    assert t.n == n
+    return t
+
+
+@pytest.mark.parametrize("solver", [pr.PGD, pr.APGD, pr.APGD_AR, pr.BBPGD, pr.BBPGDF, pr.SPG])
+@pytest.mark.parametrize("table", ["sphere3", "mixed", "soc3", "sphere_whole", "box_only"])
+def test_batched_shared_table_matches_oracle(solver, table):
+    """ccqp_solve_batched_table: ONE feasible set (any block kinds) shared by the problems of the batch -- the
+    contact-style case (friction discs = Sphere(3) blocks, solution_spaces.py:369-435, 495-560)."""
+    from helpers import op_from_table
+    n = {"sphere3": 64, "mixed": 47, "soc3": 30, "sphere_whole": 33, "box_only": 64}[table]
+    tab = {"sphere3": lambda: pr.sphere3_table(n, 0.4), "mixed": lambda: small_mixed_table(n), "soc3": lambda: pr.soc3_table(n, 0.5),
+           "sphere_whole": lambda: pr.sphere_table(n, 1.5), "box_only": lambda: pr.box_table(n, -0.3, 0.6)}[table]()
+    batch, max_mv, step, K = 32, 5000, 0.1, 512
+    tol = 1e-6 if solver in (pr.APGD, pr.APGD_AR) else 1e-8
+    A = np.empty((batch, n, n))
+    b = np.empty((batch, n))
+    for i in range(batch):
+        A[i], b[i] = pr.shift_problem(n, 700 + i, 1.0)
+    x0 = 0.3 * np.random.default_rng(11).standard_normal((batch, n)) if table == "mixed" else None
+    s = make_solver(solver, tol, max_mv, step)
+    s.solve_batched(A, b, x0=x0, seeds=np.arange(batch), n_uniforms=K, convex_proj_op=op_from_table(tab))
+    same = 0
+    for i in range(batch):
+        o = orc.solve(solver, A[i], b[i], x0=None if x0 is None else x0[i], blocks=tab.blocks, params=tab.params, tol=tol,
+                      max_mv=max_mv, step_size=step, uniforms=pr.spg_uniforms(i, K))
+        assert bool(s.solution_converged[i]) == o["converged"]
+        mv = int(s.solution_num_matrix_vector_multiplications[i])
+        scale = max(np.linalg.norm(o["solution"]), 1e-300)
+        if mv == o["mv"]:
+            same += 1
+            assert np.linalg.norm(s.solution[i] - o["solution"]) <= 1e-9 * scale
+        else:
+            assert abs(mv - o["mv"]) <= max(2, round(0.1 * o["mv"])), (i, mv, o["mv"])
+            assert np.linalg.norm(s.solution[i] - o["solution"]) <= 1e-5 * scale
+    assert same >= 0.9 * batch, (same, batch)
+
+
+def test_batched_shared_table_errors_and_device():
+    import torch
+    from ccqppy_b200 import _capi, solution_spaces as ss
+    n, batch = 12, 8
+    A = np.stack([pr.shift_problem(n, i)[0] for i in range(batch)])
+    b = np.stack([pr.shift_problem(n, i)[1] for i in range(batch)])
+    op = ss.DisjointProjOp(*[ss.SphereProjOp(3, 0.5) for _ in range(4)])
+    with pytest.raises(_capi.CCQPError):            # batched MPRGP: Box per problem only
+        make_solver(pr.MPRGP, 1e-8, 100).solve_batched(A, b, convex_proj_op=op)
+    with pytest.raises(ValueError):
+        make_solver(pr.BBPGD, 1e-8, 100).solve_batched(A, b, np.zeros((batch, n)), np.ones((batch, n)), convex_proj_op=op)
+    with pytest.raises(ValueError):
+        make_solver(pr.BBPGD, 1e-8, 100).solve_batched(A, b, convex_proj_op=ss.SphereProjOp(5, 1.0))
+    h = make_solver(pr.BBPGD, 1e-8, 1000).solve_batched(A, b, convex_proj_op=op)
+    d = make_solver(pr.BBPGD, 1e-8, 1000).solve_batched(torch.from_numpy(A).cuda(), torch.from_numpy(b).cuda(), convex_proj_op=op)
+    assert d.solution.is_cuda and np.array_equal(d.solution.cpu().numpy(), np.asarray(h.solution))
+    # every disc constraint holds
+    x = np.asarray(h.solution).reshape(batch, 4, 3)
+    assert (np.linalg.norm(x, axis=2) <= 0.5 * (1 + 1e-12)).all()
