@@ -148,7 +148,8 @@ class Handle:
         return out.value
 
     PROBES = ("dfma", "dadd", "dmul", "shfl64_dadd", "div_dadd", "sqrt_dadd", "lds128_bcast_dadd", "lds128_distinct_dadd",
-              "sts_bar_lds_dadd_bar", "bar64", "dsetp_sel_dadd")
+              "sts_bar_lds_dadd_bar", "bar64", "dsetp_sel_dadd", "dmma884_dependent", "dmma884_x8_independent_plus_8_dadd",
+              "warpsum_dmma_dadd_dmma", "warpsum_5_shfl64_dadd", "dmma_x8_with_dfma_x8")
 
     def microbench(self):
         """SM cycles per dependent operation (ccqp_microbench), as a dict."""

@@ -93,6 +93,7 @@ struct BatchedCtx {
     int tma_ok;             // rows of A can be moved with 16-byte bulk copies (8n % 16 == 0, 16-byte aligned base)
     int vec_ok;             // rows of A can be read with 256-bit loads (n % 4 == 0, 32-byte aligned base)
     int pf_ok;              // whole problems can be bulk-prefetched into L2 (16-byte granularity)
+    int vtma_ok;            // b / lb / ub rows can be moved with 16-byte bulk copies (n even, 16-byte aligned bases)
     double tol, max_mv, step, tau, sig1, sig2;
     double thr_lt;          // q <  thr_lt  <=>  sqrt(q) <  tol      (solvers.py:156 etc.)
     double thr_le;          // q <= thr_le  <=>  sqrt(q) <= tol      (SPG, solvers.py:949)
@@ -101,17 +102,20 @@ struct BatchedCtx {
 };
 
 constexpr int kBPitch = kBN + 2;        // tile row pitch (doubles): 528 bytes, conflict-free LDS.128 register fill
+template <bool GEN>
 struct BatchedSmem {
 #if CCQP_BATCHED_STAGE
     double tile[kBN * kBPitch];   // the NEXT problem's A, landed by TMA while the current one iterates
+    double vstage[3][kBN];        // ... and its b / lower / upper bounds (same mbarrier)
 #endif
     double xs[2][kBXs];     // mat-vec input, double buffered; slices padded by 16 bytes (16-byte aligned)
     double red[2][2][4];    // [parity][warp][slot]
-    double pj[2][kBN];      // general table: the vector being projected, for the members of norm blocks
+    double pj[GEN ? 2 : 1][GEN ? kBN : 2];   // general table: the vector being projected, for the members of norm blocks
 #if CCQP_BATCHED_STAGE
     uint64_t mbar;
 #endif
-    int next;
+    int next;               // the problem after the next one (fetched during the solve of the current one)
+    int first;              // prologue: this CTA's first problem
 };
 
 // Shared-memory accesses of the solver loop go through 32-bit shared-space addresses computed once
@@ -141,10 +145,55 @@ __device__ __forceinline__ double shfl_xor_f64(double v, int mask) { return __sh
 // Sum K (<= 4) values over the 64 threads; result in every thread; ONE __syncthreads.
 // Exchange butterfly: after the first stages each lane carries ONE of the K sums, so the tree
 // costs max(K,2)+3 shuffles and adds instead of 5K.  Fixed order => deterministic.
+#ifndef CCQP_BATCHED_DMMA
+#define CCQP_BATCHED_DMMA 0     // 1: the 32-lane sums of cta64_sum run on the FP64 tensor path (2 DMMA.8x8x4 + 1 DADD per sum)
+#endif
+// D(8x8) = A(8x4) B(4x8) + C, FP64 (SASS DMMA.8x8x4): lane l holds A[l/4][l%4], B[l%4][l/4], C/D[l/4][2(l%4)], [2(l%4)+1]
+__device__ __forceinline__ void dmma884_ones(double& d0, double& d1, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};"
+                 : "=d"(d0), "=d"(d1) : "d"(1.0), "d"(b), "d"(0.0), "d"(0.0));
+}
+
 template <int K>
 __device__ __forceinline__ void cta64_sum(double (&a)[K], const BShared& sh, int& parity) {
     static_assert(K >= 1 && K <= 4, "K");
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#if CCQP_BATCHED_DMMA
+    // With A = ones the first product leaves the sums of the 8 quads of lanes (a lane receives the two quads of ITS octet
+    // l%4), one add makes the octet sums, and the second product adds the four octets: the warp total in every lane.
+    // K independent chains, 2 DMMA + 1 DADD deep, against 5 dependent SHFL.64 + DADD stages; fixed order => deterministic.
+    {
+        double p[K], e0, e1;
+#pragma unroll
+        for (int j = 0; j < K; ++j) { dmma884_ones(e0, e1, a[j]); p[j] = e0 + e1; }
+#pragma unroll
+        for (int j = 0; j < K; ++j) { dmma884_ones(e0, e1, p[j]); p[j] = e0; }
+        const uint32_t base = sh.red + (uint32_t)parity * 64u;
+        if (lane < K) {
+            double v = p[0];
+#pragma unroll
+            for (int j = 1; j < K; ++j) v = (lane == j) ? p[j] : v;
+            sts_f64(base + (uint32_t)(warp * 4 + lane) * 8u, v);
+        }
+        __syncthreads();
+        if constexpr (K == 1) {
+            a[0] = lds_f64(base) + lds_f64(base + 32);
+        } else {
+            double p0, p1, q0, q1;
+            lds_f64x2(base, p0, p1);
+            lds_f64x2(base + 32, q0, q1);
+            a[0] = p0 + q0; a[1] = p1 + q1;
+            if constexpr (K == 3) a[2] = lds_f64(base + 16) + lds_f64(base + 48);
+            if constexpr (K == 4) {
+                lds_f64x2(base + 16, p0, p1);
+                lds_f64x2(base + 48, q0, q1);
+                a[2] = p0 + q0; a[3] = p1 + q1;
+            }
+        }
+        parity ^= 1;
+        return;
+    }
+#endif
     double v;
     int slot;            // which of the K sums this lane ends up carrying (lanes 0..3 are used)
     if constexpr (K == 1) {
@@ -603,7 +652,7 @@ constexpr int batched_min_ctas(int solver) {
 
 template <int SOLVER, bool WREG, bool GEN>
 __global__ void __launch_bounds__(kBN, GEN ? 5 : batched_min_ctas(SOLVER)) batched_kernel(const BatchedCtx c) {
-    __shared__ __align__(16) BatchedSmem sm;
+    __shared__ __align__(16) BatchedSmem<GEN> sm;
     const int t = threadIdx.x, n = c.n;
     const int cb = t & (kBRows - 1), row0 = kBRows * (t >> kBLog), col0 = kBCols * cb;
     int par = 0, xpar = 0;
@@ -620,18 +669,26 @@ __global__ void __launch_bounds__(kBN, GEN ? 5 : batched_min_ctas(SOLVER)) batch
     };
 #if CCQP_BATCHED_STAGE
     const bool staged = c.tma_ok != 0;
+    const bool vstaged = staged && c.vtma_ok != 0;
     unsigned phase = 0;
     if (t == 0) { mbar_init(&sm.mbar, 1); mbar_fence_init(); }
-    auto issue_load = [&](int prob) {       // one 8n-byte bulk copy per row into the padded tile, one mbarrier
-        if (t == 0) mbar_expect_tx(&sm.mbar, (uint32_t)(prob_elems * 8));
+    auto issue_load = [&](int prob) {       // one 8n-byte bulk copy per row into the padded tile (+ 3 for the vectors), one mbarrier
+        if (t == 0) mbar_expect_tx(&sm.mbar, (uint32_t)(prob_elems * 8) + (vstaged ? 3u * (uint32_t)(n * 8) : 0u));
         if (t < n) bulk_g2s(sm.tile + t * kBPitch, c.A + (size_t)prob * prob_elems + (size_t)t * n, (uint32_t)(n * 8), &sm.mbar);
+        if (vstaged && t >= kBN - 3) {      // three otherwise idle-ish threads (the mbarrier's expect_tx is program-ordered only in thread 0,
+            const int w = t - (kBN - 3);    // but a complete_tx that arrives first just drives the pending count negative: legal)
+            const double* src = w == 0 ? c.b + (size_t)prob * n : (w == 1 ? c.lb : c.ub) + (size_t)prob * c.bound_stride;
+            bulk_g2s(sm.vstage[w], src, (uint32_t)(n * 8), &sm.mbar);
+        }
     };
 #else
-    const bool staged = false;
+    const bool staged = false, vstaged = false;
 #endif
-    if (t == 0) sm.next = (int)atomicAdd(c.counter, 1u);
+    // Work queue, two problems deep: `cur` is being solved, `nxt` is known (its A is in flight), and the index after that is
+    // fetched by thread 0 at the start of a solve and published at its end -- the atomic's round trip hides behind the solve.
+    if (t == 0) { sm.first = (int)atomicAdd(c.counter, 1u); sm.next = (int)atomicAdd(c.counter, 1u); }
     __syncthreads();
-    int cur = sm.next;
+    int cur = sm.first;
 #if CCQP_BATCHED_STAGE
     if (staged && cur < c.batch) { fence_proxy_async(); issue_load(cur); }
 #endif
@@ -639,6 +696,10 @@ __global__ void __launch_bounds__(kBN, GEN ? 5 : batched_min_ctas(SOLVER)) batch
         // ---- register fill: this thread's sub-block; register row r <- row row0 + (r ^ cb) (see matvec)
         double a[kBRows][kBCols];
         const double* Ap = c.A + (size_t)cur * prob_elems;
+        BState s;
+        s.act = t < n;
+        const size_t vo = (size_t)cur * n + t;
+        const size_t bo = (size_t)cur * c.bound_stride + t;
         if (staged) {
 #if CCQP_BATCHED_STAGE
             mbar_wait(&sm.mbar, phase);
@@ -652,6 +713,11 @@ __global__ void __launch_bounds__(kBN, GEN ? 5 : batched_min_ctas(SOLVER)) batch
                     if (row < n && col0 + j < n) lds_f64x2(tb + (uint32_t)(row * kBPitch + col0 + j) * 8u, a[r][j], a[r][j + 1]);
                     else { a[r][j] = 0.0; a[r][j + 1] = 0.0; }
                 }
+            }
+            if (vstaged) {
+                s.b = s.act ? sm.vstage[0][t] : 0.0;
+                s.lo = s.act ? sm.vstage[1][t] : 0.0;
+                s.hi = s.act ? sm.vstage[2][t] : 0.0;
             }
 #endif
         } else if (c.vec_ok) {
@@ -674,15 +740,11 @@ __global__ void __launch_bounds__(kBN, GEN ? 5 : batched_min_ctas(SOLVER)) batch
                 for (int j = 0; j < kBCols; ++j)
                     a[r][j] = (row0 + (r ^ cb) < n && col0 + j < n) ? ldg_stream(Ap + (size_t)(row0 + (r ^ cb)) * n + col0 + j) : 0.0;
         }
-        __syncthreads();                       // everyone has read sm.next and, if staged, its part of the tile
-        if (t == 0) sm.next = (int)atomicAdd(c.counter, 1u);
-        BState s;
-        s.act = t < n;
-        const size_t vo = (size_t)cur * n + t;
-        const size_t bo = (size_t)cur * c.bound_stride + t;
-        s.b = s.act ? c.b[vo] : 0.0;
-        s.lo = s.act ? c.lb[bo] : 0.0;
-        s.hi = s.act ? c.ub[bo] : 0.0;
+        if (!vstaged) {
+            s.b = s.act ? c.b[vo] : 0.0;
+            s.lo = s.act ? c.lb[bo] : 0.0;
+            s.hi = s.act ? c.ub[bo] : 0.0;
+        }
         if constexpr (GEN) {
             s.kind = s.act ? c.ekind[t] : kIdentity;
             s.boff = s.act ? c.eoff[t] : 0; s.bdim = s.act ? c.edim[t] : 0; s.bnk = s.act ? c.enk[t] : 0;
@@ -691,21 +753,24 @@ __global__ void __launch_bounds__(kBN, GEN ? 5 : batched_min_ctas(SOLVER)) batch
         }
         s.x0 = (s.act && c.x0) ? c.x0[vo] : 0.0;
         s.cs = 1.0 / (3 * (double)n * kGd);
-        __syncthreads();
-        const int nxt = sm.next;
+        __syncthreads();                       // everyone has read its part of the tile / the staged vectors; sm.next (written by
+        const int nxt = sm.next;               // thread 0 at the end of the previous solve) is visible
+        unsigned after = 0;
         if (nxt < c.batch) {                   // the next problem travels while this one iterates
 #if CCQP_BATCHED_STAGE
             if (staged) { fence_proxy_async(); issue_load(nxt); } else
 #endif
             prefetch_l2(nxt);
-        }
+            if (c.x0 && s.act) asm volatile("prefetch.global.L2 [%0];" ::"l"(c.x0 + (size_t)nxt * n + t));
+            if (t == 0) after = atomicAdd(c.counter, 1u);     // consumed at the end of the solve
+        } else if (t == 0) after = (unsigned)c.batch;
 
         double xsol = 0.0;
         BatchedOut o;
         solve_one<SOLVER, WREG, GEN>(c, a, sh, s, c.uniforms ? c.uniforms + (size_t)cur * c.n_uniforms : nullptr, par, xpar,
                                      xsol, o);
         if (s.act) c.x_out[vo] = xsol;
-        if (t == 0) c.out[cur] = o;
+        if (t == 0) { c.out[cur] = o; sm.next = (int)after; }   // everybody read the old value right after the barrier above
         cur = nxt;
     }
 }
@@ -832,6 +897,7 @@ inline int batched_solve(cudaStream_t stream, int sm_count, const BatchedTable* 
     c.tma_ok = ((n * 8) % 16 == 0 && (reinterpret_cast<uintptr_t>(c.A) & 15) == 0) ? 1 : 0;
     c.vec_ok = (n % 4 == 0 && (reinterpret_cast<uintptr_t>(c.A) & 31) == 0) ? 1 : 0;
     c.pf_ok = ((n * n * 8) % 16 == 0 && (reinterpret_cast<uintptr_t>(c.A) & 15) == 0) ? 1 : 0;
+    c.vtma_ok = (n % 2 == 0 && ((reinterpret_cast<uintptr_t>(c.b) | reinterpret_cast<uintptr_t>(c.lb) | reinterpret_cast<uintptr_t>(c.ub)) & 15) == 0) ? 1 : 0;
     c.tol = prm.tol; c.max_mv = prm.max_mv; c.step = prm.step_size;
     c.tau = prm.tau; c.sig1 = prm.sigma1; c.sig2 = prm.sigma2; c.m = prm.m;
     c.thr_lt = sqrt_threshold(prm.tol, true);

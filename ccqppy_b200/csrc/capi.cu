@@ -255,6 +255,12 @@ void fill_ctx(ccqp_handle* h, DenseCtx& c, const Tiling& t) {
     c.CW = t.CW; c.SW = t.SW; c.np = t.np; c.nseg = t.nseg; c.rows_max = t.rows_max; c.psum_accum = t.accum;
     c.evict_first = ((double)h->nrows * (double)h->n * 8.0 > 96.0 * 1024 * 1024) ? 1 : 0;
     c.evict_first = env_int("CCQP_EVICT_FIRST", c.evict_first, ok_bool);
+    {   // a shard larger than L2: keep a fixed slice of it resident (same tasks every mat-vec), stream the rest evict-first
+        const double shard = (double)h->nrows * (double)h->n * 8.0;
+        const int mb = env_int("CCQP_L2_RESIDENT_MB", 64, [](int v) { return v >= 0 && v <= 120; });
+        const double f = shard > 0 ? (double)mb * 1024.0 * 1024.0 / shard : 0.0;
+        c.resident_256 = (int)std::min(256.0, std::floor(f * 256.0 + 0.5));
+    }
 }
 
 constexpr int op_slot(int op) { return op < 100 ? op : 7 + (op - 100); }   // OP_PROJGRAD -> bit 10

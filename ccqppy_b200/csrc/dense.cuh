@@ -85,6 +85,8 @@ struct DenseCtx {
     int nseg;           // total segments per row
     int rows_max;       // max rows owned by one CTA
     int evict_first;    // stream A with L2 evict-first
+    int resident_256;   // ... except the first resident_256/256 of every CTA's (row, segment) tasks, which keep the normal policy
+                        // and so stay in L2 from one mat-vec to the next (a fixed ~70 MB slice of A never touches HBM again)
     int psum_accum;     // nseg counts the segments of ONE panel; the panels' partial sums are added up in panel order
     // test hooks
     const double* hook_in;
@@ -256,8 +258,10 @@ __device__ __forceinline__ double dot_seg_generic(const double* __restrict__ aro
 //     for banded rows a warp-level gather covers 32 consecutive columns = 8 full sectors), multiplies and writes
 //     the products IN PLACE over the values; after ONE barrier per tile groups of csr_group lanes sum the rows
 //     that end inside the tile straight from shared memory (stride csr_group, then a shuffle tree).  A row that
-//     continues into the next tile leaves its partial sum in a carry slot.  The barrier of tile t+1 also proves
-//     that everybody is done with tile t, whose stage thread 0 then refills with tile t + kCsrStages.
+//     continues into the next tile leaves its partial sum in a carry slot.  The steps are software-pipelined: the
+//     gather of tile t+1 is issued BEFORE the rows of tile t are summed and consumed after, so the L2 latency of
+//     the gather hides behind the row sums.  The barrier that ends step t also proves that everybody is done with
+//     tile t, whose stage thread 0 then refills with tile t + kCsrStages.
 //   Summation order per row: tile by tile, inside a tile lane by lane + fixed tree; tile boundaries do not depend
 //   on the launch shape.  The stream's final tile, if its length is not a multiple of 4 entries (bulk copies move
 //   multiples of 16 bytes), is read with ordinary loads.
@@ -304,48 +308,71 @@ __device__ __forceinline__ void gemv_phase_csr(Kst& k, const DenseCtx& c, const 
         if (tid == 0) {
             carry_slot[0] = 0.0;
             fence_proxy_async();
-            for (int t = 0; t < nt && t < kCsrStages - 1; ++t) issue(t);
+            for (int t = 0; t < nt && t < kCsrStages; ++t) issue(t);
         }
+        // Software pipeline over the tiles: the gather of tile t+1 is IN FLIGHT (16 loads per thread, in registers)
+        // while the rows of tile t are summed; then the products of t+1 are formed and ONE barrier closes the step.
+        int j[kCsrE];
+        double x[kCsrE];
+        long long pv = 0, pv_last = 0;
+        auto tile_rows = [&](int t, int& r_cur, int& r_last) {        // rows r_cur (open since tile t-1, or the CTA's first) .. r_last
+            const long long T = (g0 + t) * kCsrTile;
+            r_cur = t == 0 ? cr0 : c.csr_tile_row[g0 + t];
+            r_last = c.csr_tile_row[g0 + t + 1];
+            if (r_last > cr1 - 1 || T + tile_count(t) >= P1) r_last = cr1 - 1;
+        };
+        auto slow_tile = [&](int t) { return (tile_count(t) & 3) || !c.csr_tma; };     // CTA-uniform
+        auto gather_issue = [&](int t) {
+            const int st = t % kCsrStages;
+            int r_cur, r_last;
+            tile_rows(t, r_cur, r_last);
+            // row pointers r_cur .. r_cur + 256 of the tile -> shared window (stored by finish_products): one coalesced load
+            pv = r_cur + tid <= cr1 ? c.csr_ptr[r_cur + tid] : 0;
+            pv_last = (tid == 0 && r_cur + kDenseThreads <= cr1) ? c.csr_ptr[r_cur + kDenseThreads] : 0;
+            if (slow_tile(t)) return;
+            const int cnt = tile_count(t);
+            const int* idx = reinterpret_cast<const int*>(ring + (size_t)st * kCsrStageBytes + kCsrTile * 8);
+            mbar_wait(&k.sm.mbar[st], k.par[st]);
+            k.par[st] ^= 1u;
+#pragma unroll
+            for (int u = 0; u < kCsrE; ++u) { const int q = u * kDenseThreads + tid; j[u] = q < cnt ? idx[q] : 0; }
+#pragma unroll
+            for (int u = 0; u < kCsrE; ++u) x[u] = c.csr_l1 ? ld_ca(v + j[u]) : ld_cg(v + j[u]);
+        };
+        auto finish_products = [&](int t) {
+            const int st = t % kCsrStages;
+            const long long T = (g0 + t) * kCsrTile;
+            const int cnt = tile_count(t);
+            double* prod = reinterpret_cast<double*>(ring + (size_t)st * kCsrStageBytes);
+            long long* pw = win + (t & 1) * kCsrWin;
+            pw[tid] = pv;
+            if (tid == 0) pw[kDenseThreads] = pv_last;
+            if (slow_tile(t)) {                                       // ragged final tile of the stream / unaligned arrays
+                for (int q = tid; q < cnt; q += kDenseThreads) {
+                    const double xv = c.csr_l1 ? ld_ca(v + __ldg(c.csr_idx + T + q)) : ld_cg(v + __ldg(c.csr_idx + T + q));
+                    prod[q] = ldg_stream(c.csr_val + T + q) * xv;
+                }
+            } else {
+#pragma unroll
+                for (int u = 0; u < kCsrE; ++u) { const int q = u * kDenseThreads + tid; if (q < cnt) prod[q] *= x[u]; }
+            }
+        };
+        gather_issue(0);
+        finish_products(0);
+        __syncthreads();
         for (int t = 0; t < nt; ++t) {
             const int st = t % kCsrStages;
             const long long T = (g0 + t) * kCsrTile;
             const int cnt = tile_count(t);
             const long long t0 = T > P0 ? T : P0, t1 = T + cnt < P1 ? T + cnt : P1;     // this CTA's entries of the tile
-            // rows of the tile: r_cur (open since the previous tile, or this CTA's first row) ... r_last
-            int r_cur = t == 0 ? cr0 : c.csr_tile_row[g0 + t], r_last = c.csr_tile_row[g0 + t + 1];
-            if (r_last > cr1 - 1 || T + cnt >= P1) r_last = cr1 - 1;
+            int r_cur, r_last;
+            tile_rows(t, r_cur, r_last);
             const int nrows_t = r_last - r_cur + 1;
-            long long* pw = win + (t & 1) * kCsrWin;
-            // row pointers r_cur .. r_cur + 256 of this tile -> shared window: one coalesced load, issued here, stored
-            // after the gather has been issued (so the loads travel together)
-            const long long pv = r_cur + tid <= cr1 ? c.csr_ptr[r_cur + tid] : 0;
-            const long long pv_last = (tid == 0 && r_cur + kDenseThreads <= cr1) ? c.csr_ptr[r_cur + kDenseThreads] : 0;
-            double* prod = reinterpret_cast<double*>(ring + (size_t)st * kCsrStageBytes);
-            const int* idx = reinterpret_cast<const int*>(ring + (size_t)st * kCsrStageBytes + kCsrTile * 8);
-            if ((cnt & 3) || !c.csr_tma) {                            // CTA-uniform
-                for (int q = tid; q < cnt; q += kDenseThreads) {
-                    const double x = c.csr_l1 ? ld_ca(v + __ldg(c.csr_idx + T + q)) : ld_cg(v + __ldg(c.csr_idx + T + q));
-                    prod[q] = ldg_stream(c.csr_val + T + q) * x;
-                }
-            } else {
-                mbar_wait(&k.sm.mbar[st], k.par[st]);
-                k.par[st] ^= 1u;
-                int j[kCsrE];
-                double x[kCsrE];
-#pragma unroll
-                for (int u = 0; u < kCsrE; ++u) { const int q = u * kDenseThreads + tid; j[u] = q < cnt ? idx[q] : 0; }
-#pragma unroll
-                for (int u = 0; u < kCsrE; ++u) x[u] = c.csr_l1 ? ld_ca(v + j[u]) : ld_cg(v + j[u]);
-                pw[tid] = pv;
-                if (tid == 0) pw[kDenseThreads] = pv_last;
-#pragma unroll
-                for (int u = 0; u < kCsrE; ++u) { const int q = u * kDenseThreads + tid; if (q < cnt) prod[q] *= x[u]; }
-            }
-            if ((cnt & 3) || !c.csr_tma) { pw[tid] = pv; if (tid == 0) pw[kDenseThreads] = pv_last; }
-            __syncthreads();          // products + row-pointer window of this tile and the carry of the previous one are visible;
-                                      // everybody has finished the previous tile, whose stage can be refilled
+            const long long* pw = win + (t & 1) * kCsrWin;
+            const double* prod = reinterpret_cast<const double*>(ring + (size_t)st * kCsrStageBytes);
+            // everybody is behind the barrier that ended step t-1: the stage of tile t-1 is free
             if (tid == 0 && t >= 1 && t - 1 + kCsrStages < nt) { fence_proxy_async(); issue(t - 1 + kCsrStages); }
-            if (tid == 0 && t == 0 && kCsrStages - 1 < nt) { fence_proxy_async(); issue(kCsrStages - 1); }
+            if (t + 1 < nt) gather_issue(t + 1);
             const double carry_in = carry_slot[t & 1];
             for (int kk = 0; kk * ngroups < nrows_t; ++kk) {          // CTA-uniform trip count
                 const int i = gid + kk * ngroups, r = r_cur + i;
@@ -371,6 +398,9 @@ __device__ __forceinline__ void gemv_phase_csr(Kst& k, const DenseCtx& c, const 
                     else carry_slot[(t + 1) & 1] = acc;               // the one row that continues into the next tile (r_last)
                 }
             }
+            if (t + 1 < nt) finish_products(t + 1);
+            __syncthreads();          // products + row-pointer window of tile t+1 and the carry of tile t are visible;
+                                      // everybody has finished tile t
         }
     } else {
         for (int r = cr0 + tid; r < cr1; r += kDenseThreads) epi(c.row0 + r, 0.0);     // a range of empty rows
@@ -408,14 +438,15 @@ __device__ __forceinline__ void gemv_phase(Kst& k, const DenseCtx& c, const doub
         const int spp = (pc + SW - 1) / SW;
         const int ntask = nrows_cta * spp;
         const double* vb = k.sm.vbuf[buf];
+        const int t_res = c.evict_first ? (int)(((long long)ntask * c.resident_256) >> 8) : ntask;   // tasks [0, t_res) stay in L2
         for (int t = warp; t < ntask; t += kDenseWarps) {
             const int row = t / spp, seg = t - row * spp;
             const int col0 = seg * SW;
             const int ncol = min(SW, pc - col0);
             const double* arow = c.A + (size_t)(k.r0 - c.row0 + row) * c.lda + (size_t)p * CW + col0;
             double acc;
-            if (c.aligned) acc = c.evict_first ? dot_seg_aligned<true>(arow, vb + col0, ncol, lane)
-                                               : dot_seg_aligned<false>(arow, vb + col0, ncol, lane);
+            if (c.aligned) acc = t >= t_res ? dot_seg_aligned<true>(arow, vb + col0, ncol, lane)
+                                            : dot_seg_aligned<false>(arow, vb + col0, ncol, lane);
             else acc = dot_seg_generic(arow, vb + col0, ncol, lane);
             acc = warp_sum(acc);
             if (lane == 0) {

@@ -32,8 +32,23 @@ constexpr int kPeakFmaPerIter = 64;         // per thread per loop trip
 
 enum ProbeKind : int {
     PROBE_DFMA = 0, PROBE_DADD, PROBE_DMUL, PROBE_SHFL_DADD, PROBE_DIV, PROBE_SQRT, PROBE_LDS128_BCAST, PROBE_LDS128_DISTINCT,
-    PROBE_STS_BAR_LDS, PROBE_BAR, PROBE_DSETP_SEL, PROBE_COUNT
+    PROBE_STS_BAR_LDS, PROBE_BAR, PROBE_DSETP_SEL, PROBE_DMMA, PROBE_DMMA_X8, PROBE_WARPSUM_DMMA, PROBE_WARPSUM_SHFL,
+    PROBE_DMMA_X8_DFMA_X8, PROBE_COUNT
 };
+
+// D(8x8) = A(8x4) B(4x8) + C on the FP64 tensor path (SASS DMMA.884): lane l holds A[l/4][l%4], B[l%4][l/4],
+// C/D[l/4][2(l%4)], [2(l%4)+1]
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b, double c0, double c1) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};"
+                 : "=d"(d0), "=d"(d1) : "d"(a), "d"(b), "d"(c0), "d"(c1));
+}
+// sum of v over the 32 lanes of a warp in 2 DMMAs + 1 DADD (A = ones): quad sums, pair-of-quad sums, total
+__device__ __forceinline__ double warp_sum_dmma(double v) {
+    double d0, d1, e0, e1;
+    dmma884(d0, d1, 1.0, v, 0.0, 0.0);
+    dmma884(e0, e1, 1.0, d0 + d1, 0.0, 0.0);
+    return e0;
+}
 
 // cycles[kind] = clock64() ticks of `reps` dependent operations executed by warp 0 of a 64-thread CTA
 __global__ void __launch_bounds__(64) probe_kernel(long long* cycles, double* sink, int reps, double x, double y) {
@@ -71,6 +86,41 @@ __global__ void __launch_bounds__(64) probe_kernel(long long* cycles, double* si
     PROBE(PROBE_STS_BAR_LDS, { sh[t] = v; __syncthreads(); v = sh[(t + 1) & 63] + 1.0; __syncthreads(); })
     PROBE(PROBE_BAR, __syncthreads())
     PROBE(PROBE_DSETP_SEL, v = (v < w) ? w : v + 1.0)
+    double keep = v;                          // every probe's result reaches the sink (nothing is dead code)
+    v = 1.0 + 1e-9 * t;
+    { double d0, d1; PROBE(PROBE_DMMA, { dmma884(d0, d1, 0.25, v, 0.0, 0.0); v = d0; }) }
+    {
+        double d[8][2];
+        PROBE(PROBE_DMMA_X8, {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) dmma884(d[u][0], d[u][1], 0.25, v + u, 0.0, 0.0);
+            v = d[0][0] * 1e-3;
+#pragma unroll
+            for (int u = 1; u < 8; ++u) v += d[u][1] * 1e-9;
+        })
+    }
+    keep += v;
+    v = 1.0 + 1e-9 * t;
+    PROBE(PROBE_WARPSUM_DMMA, v = warp_sum_dmma(v) * 0.03125)
+    PROBE(PROBE_WARPSUM_SHFL, {
+        v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2); v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 8); v += __shfl_xor_sync(0xffffffffu, v, 16); v *= 0.03125; })
+    {
+        double d[8][2], f[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) f[u] = v + u;
+        PROBE(PROBE_DMMA_X8_DFMA_X8, {          // do DMMA and DFMA share an issue path?  8 + 8 independent per trip
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { dmma884(d[u][0], d[u][1], 0.25, f[u], 0.0, 0.0); f[u] = fma(f[u], w, w); }
+            v = d[0][0] * 1e-3;
+#pragma unroll
+            for (int u = 1; u < 8; ++u) v += d[u][1] * 1e-9;
+            f[0] += v * 1e-9;
+        })
+#pragma unroll
+        for (int u = 0; u < 8; ++u) keep += f[u];
+    }
+    v += keep;
 #undef PROBE
     sink[t] = v;
 }

@@ -226,7 +226,8 @@ ccqp_status ccqp_debug_divide(ccqp_handle* h, const double* a0, const double* a1
 ccqp_status ccqp_fp64_peak(ccqp_handle* h, int blocks_per_sm, int threads_per_block, double* tflops);
 /* SM cycles per dependent operation, one warp, in the order DFMA, DADD, DMUL, SHFL.64+DADD, IEEE
  * division+DADD, sqrt+DADD, LDS.128 (all lanes one address)+DADD, LDS.128 (distinct)+DADD,
- * STS+bar+LDS+DADD+bar, bar.sync (64 threads), DSETP+select+DADD.  n_out >= 11.  Feeds the cycle
+ * STS+bar+LDS+DADD+bar, bar.sync (64 threads), DSETP+select+DADD, then the FP64 tensor path (DMMA.884 dependent,
+ * 8 independent, a 32-lane sum as DMMA+DADD+DMMA against 5 shuffle stages, DMMA mixed with DFMA).  n_out >= 16.  Feeds the cycle
  * model of the batched kernel in DESIGN.md. */
 ccqp_status ccqp_microbench(ccqp_handle* h, double* cycles_per_op, int32_t n_out);
 
