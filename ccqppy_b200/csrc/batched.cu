@@ -18,13 +18,13 @@ int batched_solve_table_entry(cudaStream_t stream, int sm_count, int solver, con
                               const double* params, long long n_params, const double* uniforms, long long n_uniforms, double* x_out,
                               int memtype, ccqp_result* results, ccqp_result* summary, cudaEvent_t ev0, cudaEvent_t ev1, int* launches,
                               std::string& err, const std::function<void*(size_t)>& alloc) {
-    // the same validation and per-element expansion as ccqp_set_projection (capi.cu), for a table of n <= 64 unknowns
-    if (n > kBN) return CCQP_ERR_UNSUPPORTED;
+    // the same validation and per-element expansion as ccqp_set_projection (capi.cu), for a table of n <= 128 unknowns
+    if (n > kBNMax) return CCQP_ERR_UNSUPPORTED;
     BatchedTable tab;
     const double inf = INFINITY;
-    tab.lo.assign(kBN, -inf); tab.hi.assign(kBN, inf); tab.epar.assign(kBN, 0.0);
-    tab.ekind.assign(kBN, (uint8_t)kIdentity);
-    tab.eoff.assign(kBN, 0); tab.edim.assign(kBN, 0); tab.enk.assign(kBN, 0);
+    tab.lo.assign(kBNMax, -inf); tab.hi.assign(kBNMax, inf); tab.epar.assign(kBNMax, 0.0);
+    tab.ekind.assign(kBNMax, (uint8_t)kIdentity);
+    tab.eoff.assign(kBNMax, 0); tab.edim.assign(kBNMax, 0); tab.enk.assign(kBNMax, 0);
     long long at = 0;
     for (long long k = 0; k < n_blocks; ++k) {
         const ccqp_block& bl = blocks[k];

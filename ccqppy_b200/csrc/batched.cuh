@@ -47,20 +47,30 @@
 #ifndef CCQP_BATCHED_STAGE
 #define CCQP_BATCHED_STAGE 1    // 1: A reaches the registers through a TMA-filled shared tile (next problem in flight
 #endif                          //    during the solve); 0: straight from L2 (bulk L2 prefetch of the next problem)
-#ifndef CCQP_BATCHED_ROWS
-#define CCQP_BATCHED_ROWS 8     // 8: 8x8 sub-blocks (3-stage exchange), 4: 4x16 sub-blocks (2-stage exchange)
-#endif
-
 namespace ccqp {
 
-constexpr int kBN = 64;                 // max unknowns per problem = threads per CTA
-constexpr int kBRows = CCQP_BATCHED_ROWS;    // sub-block of A held by one thread: kBRows x kBCols = 64 entries;
-constexpr int kBCols = kBN / kBRows;         // kBRows is also the number of lanes that share a row block
-constexpr int kBLog = (kBRows == 8) ? 3 : 2;
-constexpr int kBSlice = kBCols + 2;     // shared-memory pitch of one slice of the mat-vec input: consecutive slices
-                                        // start 16 bytes further into the 128-byte bank window, so the LDS.128 of
-                                        // a quarter-warp (kBRows distinct slices) is conflict-free
-constexpr int kBXs = kBRows * kBSlice;
+// Launch shape and layout of one problem.
+//   NT = 64 threads, n <= 64 (the benchmark configuration): thread t = 8 rb + cb keeps the 8 x 8 sub-block (row block rb, column
+//   block cb) of A in registers and owns unknown t.
+//   NT = 256 threads, n <= 128: thread t = 16 rb + cb, a 16 x 16 grid of 8 x 8 sub-blocks.  The 16 lanes of a row block end the
+//   mat-vec with 8 row sums, so TWO neighbouring lanes hold (and redundantly update) the same unknown 8 rb + (cb >> 1); the even
+//   lane of the pair is its owner: it publishes the entry, feeds the reductions and writes the result.
+template <int NT>
+struct BL {
+    static_assert(NT == 64 || NT == 256, "threads per problem");
+    static constexpr int N = NT == 64 ? 64 : 128;      // max unknowns per problem
+    static constexpr int NB = N / 8;                   // column blocks = lanes that share a row block
+    static constexpr int SH = NT == 64 ? 0 : 1;        // log2 of the lanes that hold one unknown
+    static constexpr int WARPS = NT / 32;
+    static constexpr int SLICE = 8 + 2;                // pitch of one 8-entry slice of the mat-vec input: consecutive slices start 16
+                                                       // bytes further into the 128-byte bank window (conflict-free LDS.128)
+    static constexpr int XS = NB * SLICE;
+    static constexpr int PITCH = N + 2;                // tile row pitch (doubles): conflict-free LDS.128 register fill
+    static constexpr uint32_t XS_BYTES = XS * 8, RED_BYTES = WARPS * 32;
+};
+constexpr int kBN = 64;                 // the small layout's limit
+constexpr int kBNMax = 128;             // largest n of the batched mode
+constexpr int kBRows = 8, kBCols = 8;   // sub-block of A held by one thread
 constexpr int kBWindow = 64;            // SPG window limit (generic path)
 constexpr int kBWinReg = 5;             // SPG window kept in registers when m == kBWinReg (the reference default)
 
@@ -101,16 +111,15 @@ struct BatchedCtx {
     int m;
 };
 
-constexpr int kBPitch = kBN + 2;        // tile row pitch (doubles): 528 bytes, conflict-free LDS.128 register fill
-template <bool GEN>
+template <bool GEN, int NT>
 struct BatchedSmem {
 #if CCQP_BATCHED_STAGE
-    double tile[kBN * kBPitch];   // the NEXT problem's A, landed by TMA while the current one iterates
-    double vstage[3][kBN];        // ... and its b / lower / upper bounds (same mbarrier)
+    double tile[BL<NT>::N * BL<NT>::PITCH];   // the NEXT problem's A, landed by TMA while the current one iterates
+    double vstage[3][BL<NT>::N];              // ... and its b / lower / upper bounds (same mbarrier)
 #endif
-    double xs[2][kBXs];     // mat-vec input, double buffered; slices padded by 16 bytes (16-byte aligned)
-    double red[2][2][4];    // [parity][warp][slot]
-    double pj[GEN ? 2 : 1][GEN ? kBN : 2];   // general table: the vector being projected, for the members of norm blocks
+    double xs[2][BL<NT>::XS];                 // mat-vec input, double buffered
+    double red[2][BL<NT>::WARPS][4];          // [parity][warp][slot]
+    double pj[GEN ? 2 : 1][GEN ? BL<NT>::N : 2];   // general table: the vector being projected, for the members of norm blocks
 #if CCQP_BATCHED_STAGE
     uint64_t mbar;
 #endif
@@ -122,11 +131,10 @@ struct BatchedSmem {
 // per thread: with generic pointers the compiler re-derives the shared window base (S2UR
 // SR_CgaCtaId + ULEA, a scoreboard stall) in front of every access of the loop.
 struct BShared {
-    uint32_t xs_wr;     // where thread t publishes its entry (buffer 0)
-    uint32_t xs_rd;     // this thread's 16-entry slice (buffer 0)
+    uint32_t xs_wr;     // where the owner of an unknown publishes its entry (buffer 0)
+    uint32_t xs_rd;     // this thread's 8-entry slice (buffer 0)
     uint32_t red;       // red[0][0][0]
 };
-constexpr uint32_t kBXsBytes = kBXs * 8;
 
 __device__ __forceinline__ void sts_f64(uint32_t addr, double v) {
     asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
@@ -154,28 +162,10 @@ __device__ __forceinline__ void dmma884_ones(double& d0, double& d1, double b) {
                  : "=d"(d0), "=d"(d1) : "d"(1.0), "d"(b), "d"(0.0), "d"(0.0));
 }
 
-template <int K>
-__device__ __forceinline__ void cta64_sum(double (&a)[K], const BShared& sh, int& parity) {
-    static_assert(K >= 1 && K <= 4, "K");
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#if CCQP_BATCHED_DMMA
-    // With A = ones the first product leaves the sums of the 8 quads of lanes (a lane receives the two quads of ITS octet
-    // l%4), one add makes the octet sums, and the second product adds the four octets: the warp total in every lane.
-    // K independent chains, 2 DMMA + 1 DADD deep, against 5 dependent SHFL.64 + DADD stages; fixed order => deterministic.
-    {
-        double p[K], e0, e1;
-#pragma unroll
-        for (int j = 0; j < K; ++j) { dmma884_ones(e0, e1, a[j]); p[j] = e0 + e1; }
-#pragma unroll
-        for (int j = 0; j < K; ++j) { dmma884_ones(e0, e1, p[j]); p[j] = e0; }
-        const uint32_t base = sh.red + (uint32_t)parity * 64u;
-        if (lane < K) {
-            double v = p[0];
-#pragma unroll
-            for (int j = 1; j < K; ++j) v = (lane == j) ? p[j] : v;
-            sts_f64(base + (uint32_t)(warp * 4 + lane) * 8u, v);
-        }
-        __syncthreads();
+// Cross-warp part of bsum: the warps' partial sums (red[parity][warp][slot]) are added in warp order
+template <int K, int NT>
+__device__ __forceinline__ void bsum_collect(double (&a)[K], uint32_t base) {
+    if constexpr (NT == 64) {
         if constexpr (K == 1) {
             a[0] = lds_f64(base) + lds_f64(base + 32);
         } else {
@@ -190,6 +180,50 @@ __device__ __forceinline__ void cta64_sum(double (&a)[K], const BShared& sh, int
                 a[2] = p0 + q0; a[3] = p1 + q1;
             }
         }
+    } else {
+        double v[BL<NT>::WARPS][4];
+#pragma unroll
+        for (int w = 0; w < BL<NT>::WARPS; ++w) {
+            lds_f64x2(base + w * 32, v[w][0], v[w][1]);
+            if constexpr (K > 2) lds_f64x2(base + w * 32 + 16, v[w][2], v[w][3]);
+        }
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            double t = v[0][j];
+#pragma unroll
+            for (int w = 1; w < BL<NT>::WARPS; ++w) t += v[w][j];
+            a[j] = t;
+        }
+    }
+}
+
+template <int K, int NT>
+__device__ __forceinline__ void bsum(double (&a)[K], const BShared& sh, int& parity, bool own) {
+    static_assert(K >= 1 && K <= 4, "K");
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if constexpr (BL<NT>::SH != 0) {        // an unknown held by two lanes counts once
+#pragma unroll
+        for (int j = 0; j < K; ++j) a[j] = own ? a[j] : 0.0;
+    }
+#if CCQP_BATCHED_DMMA
+    // With A = ones the first product leaves the sums of the 8 quads of lanes (a lane receives the two quads of ITS octet
+    // l%4), one add makes the octet sums, and the second product adds the four octets: the warp total in every lane.
+    // K independent chains, 2 DMMA + 1 DADD deep, against 5 dependent SHFL.64 + DADD stages; fixed order => deterministic.
+    {
+        double p[K], e0, e1;
+#pragma unroll
+        for (int j = 0; j < K; ++j) { dmma884_ones(e0, e1, a[j]); p[j] = e0 + e1; }
+#pragma unroll
+        for (int j = 0; j < K; ++j) { dmma884_ones(e0, e1, p[j]); p[j] = e0; }
+        const uint32_t base = sh.red + (uint32_t)parity * BL<NT>::RED_BYTES;
+        if (lane < K) {
+            double v = p[0];
+#pragma unroll
+            for (int j = 1; j < K; ++j) v = (lane == j) ? p[j] : v;
+            sts_f64(base + (uint32_t)(warp * 4 + lane) * 8u, v);
+        }
+        __syncthreads();
+        bsum_collect<K, NT>(a, base);
         parity ^= 1;
         return;
     }
@@ -222,54 +256,45 @@ __device__ __forceinline__ void cta64_sum(double (&a)[K], const BShared& sh, int
     v += shfl_xor_f64(v, 4);
     v += shfl_xor_f64(v, 8);
     v += shfl_xor_f64(v, 16);
-    const uint32_t base = sh.red + (uint32_t)parity * 64u;      // red[parity]: 2 warps x 4 slots x 8 bytes
+    const uint32_t base = sh.red + (uint32_t)parity * BL<NT>::RED_BYTES;      // red[parity]: WARPS x 4 slots x 8 bytes
     if (lane < 4 && slot < K) sts_f64(base + (uint32_t)(warp * 4 + slot) * 8u, v);
     __syncthreads();
-    if constexpr (K == 1) {
-        a[0] = lds_f64(base) + lds_f64(base + 32);
-    } else {
-        double p0, p1, q0, q1;
-        lds_f64x2(base, p0, p1);
-        lds_f64x2(base + 32, q0, q1);
-        a[0] = p0 + q0; a[1] = p1 + q1;
-        if constexpr (K == 3) a[2] = lds_f64(base + 16) + lds_f64(base + 48);
-        if constexpr (K == 4) {
-            lds_f64x2(base + 16, p0, p1);
-            lds_f64x2(base + 48, q0, q1);
-            a[2] = p0 + q0; a[3] = p1 + q1;
-        }
-    }
+    bsum_collect<K, NT>(a, base);
     parity ^= 1;
 }
 
-// bitwise AND of a 64-bit mask over the 64 threads (MPRGP's bisection); ONE __syncthreads
-__device__ __forceinline__ unsigned long long cta64_and(unsigned long long m, const BShared& sh, int& parity) {
+// bitwise AND of a 64-bit mask over the threads of the CTA (MPRGP's bisection); ONE __syncthreads
+template <int NT>
+__device__ __forceinline__ unsigned long long band(unsigned long long m, const BShared& sh, int& parity) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     m = warp_and64(m);
-    const uint32_t base = sh.red + (uint32_t)parity * 64u;
+    const uint32_t base = sh.red + (uint32_t)parity * BL<NT>::RED_BYTES;
     if (lane == 0) sts_f64(base + (uint32_t)warp * 32u, __longlong_as_double((long long)m));
     __syncthreads();
-    const unsigned long long r = (unsigned long long)__double_as_longlong(lds_f64(base)) &
-                                 (unsigned long long)__double_as_longlong(lds_f64(base + 32));
+    unsigned long long r = ~0ull;
+#pragma unroll
+    for (int w = 0; w < BL<NT>::WARPS; ++w) r &= (unsigned long long)__double_as_longlong(lds_f64(base + w * 32));
     parity ^= 1;
     return r;
 }
 
 __device__ __forceinline__ double clampd(double t, double lo, double hi) { return t < lo ? lo : (t > hi ? hi : t); }
 
-// Publish v (entry t of the mat-vec input) and return (A v)_t.
-// Thread t = kBRows*rb + cb holds the kBRows x kBCols sub-block (row block rb, column block cb).
-// Register row i holds row kBRows*rb + (i ^ cb) of A (the fill permutes the rows), so that in the
-// exchange butterfly below the partial sums a lane keeps and the ones it sends sit in FIXED
-// registers: no per-lane selects.  Stage "xor h" (h = kBRows/2, ..., 1): a lane keeps the rows whose
-// bit h agrees with its own cb and receives the partner's partial sums of exactly those rows; after
-// the last stage lane cb holds row 0 ^ cb = cb complete, i.e. thread t holds y_t.
-// `act` is false for the padding threads t >= n: they publish an exact zero whatever v is, so a
+// Publish v (this thread's unknown, as the mat-vec input) and return (A v) for that unknown.
+// Thread t = NB*rb + cb holds the 8 x 8 sub-block (row block rb, column block cb).  With key = cb >> SH (3 bits), register row
+// i holds row 8*rb + (i ^ key) of A (the fill permutes the rows), so that in the exchange butterfly below the partial sums a
+// lane keeps and the ones it sends sit in FIXED registers: no per-lane selects.  Stage h = 4, 2, 1 (lane distance h << SH): a
+// lane keeps the rows whose bit h agrees with its own key and receives the partner's partial sums of exactly those rows; after
+// the last stage the lane holds row 0 ^ key = key complete over its half of the column blocks, and (NT = 256) one more add with
+// the neighbouring lane completes it: the thread holds y for the unknown 8*rb + key it owns.
+// `act` is false for the padding (unknown index >= n): it is published as an exact zero whatever v is, so a
 // non-finite step length cannot leak NaNs into the active rows through the zero columns of A.
+template <int NT>
 __device__ __forceinline__ double matvec(const double (&a)[kBRows][kBCols], const BShared& sh, int& xpar, bool act,
                                          double v) {
-    const uint32_t boff = (uint32_t)xpar * kBXsBytes;
-    sts_f64(sh.xs_wr + boff, act ? v : 0.0);
+    constexpr int SH = BL<NT>::SH;
+    const uint32_t boff = (uint32_t)xpar * BL<NT>::XS_BYTES;
+    if (SH == 0 || !(threadIdx.x & 1)) sts_f64(sh.xs_wr + boff, act ? v : 0.0);
     __syncthreads();
     const uint32_t xp = sh.xs_rd + boff;
     xpar ^= 1;
@@ -277,38 +302,26 @@ __device__ __forceinline__ double matvec(const double (&a)[kBRows][kBCols], cons
 #pragma unroll
     for (int j = 0; j < kBCols; j += 2) lds_f64x2(xp + j * 8, x[j], x[j + 1]);
     double s[kBRows];
-    if constexpr (kBRows == 8) {      // 8 rows: one chain per row
 #pragma unroll
-        for (int r = 0; r < kBRows; ++r) s[r] = a[r][0] * x[0];
+    for (int r = 0; r < kBRows; ++r) s[r] = a[r][0] * x[0];         // one chain per row
 #pragma unroll
-        for (int j = 1; j < kBCols; ++j)
+    for (int j = 1; j < kBCols; ++j)
 #pragma unroll
-            for (int r = 0; r < kBRows; ++r) s[r] = fma(a[r][j], x[j], s[r]);
-    } else {                          // 4 rows: two chains per row
-        double acc[kBRows][2];
-#pragma unroll
-        for (int r = 0; r < kBRows; ++r) { acc[r][0] = a[r][0] * x[0]; acc[r][1] = a[r][1] * x[1]; }
-#pragma unroll
-        for (int j = 2; j < kBCols; j += 2)
-#pragma unroll
-            for (int r = 0; r < kBRows; ++r) {
-                acc[r][0] = fma(a[r][j], x[j], acc[r][0]);
-                acc[r][1] = fma(a[r][j + 1], x[j + 1], acc[r][1]);
-            }
-#pragma unroll
-        for (int r = 0; r < kBRows; ++r) s[r] = acc[r][0] + acc[r][1];
-    }
+        for (int r = 0; r < kBRows; ++r) s[r] = fma(a[r][j], x[j], s[r]);
 #pragma unroll
     for (int h = kBRows / 2; h >= 1; h >>= 1)
 #pragma unroll
-        for (int i = 0; i < h; ++i) s[i] += shfl_xor_f64(s[i + h], h);
+        for (int i = 0; i < h; ++i) s[i] += shfl_xor_f64(s[i + h], h << SH);
+    if constexpr (SH != 0) s[0] += shfl_xor_f64(s[0], 1);
     return s[0];
 }
 
 struct BState {                 // per-thread view of one problem (thread t <-> unknown t)
     double b, lo, hi, x0;
     double cs;                  // 1/(3 n gd)
-    bool act;                   // t < n
+    bool act;                   // the unknown exists (index < n)
+    bool own;                   // ... and this thread is the lane that owns it (NT = 64: the same thing)
+    int u;                      // index of the unknown
     // general table only
     int kind;                   // element kind
     int boff, bdim, bnk;        // norm block of this element
@@ -320,11 +333,12 @@ struct BState {                 // per-thread view of one problem (thread t <-> 
 // reference Cone / SOC of any dimension <= n): the vector goes through shared memory, every member reads its block and
 // forms the norm with the sequential FMA chain of project_pass (proj.cuh), then applies the block's rule to its own entry.
 // Every thread of the CTA must call it (one barrier when the table has norm blocks).
+template <int NT>
 __device__ __forceinline__ double project_general(const BState& s, bool has_norm, int& ppar, double t) {
     double p = clamp_elem(s.kind, t, s.lo, s.hi);
     if (has_norm) {
-        const uint32_t base = s.pj + (uint32_t)ppar * (kBN * 8u);
-        sts_f64(base + threadIdx.x * 8u, t);
+        const uint32_t base = s.pj + (uint32_t)ppar * (BL<NT>::N * 8u);
+        sts_f64(base + (uint32_t)s.u * 8u, t);        // (NT = 256: both lanes of an unknown store the same value)
         __syncthreads();
         if (s.kind == kElemNorm) {
             NormRule R;
@@ -338,7 +352,7 @@ __device__ __forceinline__ double project_general(const BState& s, bool has_norm
             }
             R.r = sqrt(ss); R.last = last;
             R.finish();
-            p = R.apply(t, (int)threadIdx.x == s.boff + s.bdim - 1);
+            p = R.apply(t, s.u == s.boff + s.bdim - 1);
         }
         ppar ^= 1;
     }
@@ -384,7 +398,7 @@ struct SpgWindow {
     }
 };
 
-template <int SOLVER, bool WREG, bool GEN>
+template <int SOLVER, bool WREG, bool GEN, int NT>
 __device__ __forceinline__ void solve_one(const BatchedCtx& c, const double (&a)[kBRows][kBCols], const BShared& sm,
                                           const BState& s, const double* uni, int& par, int& xpar, double& xsol,
                                           BatchedOut& o) {
@@ -393,32 +407,32 @@ __device__ __forceinline__ void solve_one(const BatchedCtx& c, const double (&a)
     const int maxmv = c.max_mv_i;
     int ppar = 0;
     // the projection: Box per problem (solution_spaces.py:363-366), or the batch's general table
-    auto P = [&](double t) { if constexpr (GEN) return project_general(s, c.has_norm != 0, ppar, t); else return clampd(t, s.lo, s.hi); };
+    auto P = [&](double t) { if constexpr (GEN) return project_general<NT>(s, c.has_norm != 0, ppar, t); else return clampd(t, s.lo, s.hi); };
     auto resid2 = [&](double x, double g) { const double d = s.cs * (x - P(x - kGd * g)); return d * d; };
 
     if constexpr (SOLVER == CCQP_SOLVER_PGD || SOLVER == CCQP_SOLVER_BBPGD || SOLVER == CCQP_SOLVER_BBPGDF) {
         // solvers.py:114-170, 606-669, 741-819
         double x = s.x0, xm = s.x0, g, gm, xmin = s.x0, gmin = s.x0, resmin = INFINITY;
-        gm = matvec(a, sm, xpar, s.act, xm) + s.b; gemv++; mv = 1;
+        gm = matvec<NT>(a, sm, xpar, s.act, xm) + s.b; gemv++; mv = 1;
         double r1[1] = {resid2(xm, gm)};
-        cta64_sum<1>(r1, sm, par);
+        bsum<1, NT>(r1, sm, par, s.own);
         double res2 = r1[0];
         if (!(res2 < c.thr_lt)) {
             double step = c.step;
             if (SOLVER != CCQP_SOLVER_PGD) {
-                const double ag = matvec(a, sm, xpar, s.act, gm); gemv++;          // not counted (:635)
+                const double ag = matvec<NT>(a, sm, xpar, s.act, gm); gemv++;          // not counted (:635)
                 double q[2] = {gm * gm, gm * ag};
-                cta64_sum<2>(q, sm, par);
+                bsum<2, NT>(q, sm, par, s.own);
                 step = q[0] / q[1];
             }
             for (;;) {
                 x = P(xm - step * gm);
-                g = matvec(a, sm, xpar, s.act, x) + s.b; gemv++; mv++;
+                g = matvec<NT>(a, sm, xpar, s.act, x) + s.b; gemv++; mv++;
                 if (mv >= maxmv) break;
                 const double sx = x - xm, sy = g - gm;
                 double q[3] = {resid2(x, g), sx * sx, sx * sy};
-                if (SOLVER == CCQP_SOLVER_PGD) { double q1[1] = {q[0]}; cta64_sum<1>(q1, sm, par); q[0] = q1[0]; }
-                else cta64_sum<3>(q, sm, par);
+                if (SOLVER == CCQP_SOLVER_PGD) { double q1[1] = {q[0]}; bsum<1, NT>(q1, sm, par, s.own); q[0] = q1[0]; }
+                else bsum<3, NT>(q, sm, par, s.own);
                 res2 = q[0];
                 iters++;
                 if (res2 < c.thr_lt) break;
@@ -429,7 +443,7 @@ __device__ __forceinline__ void solve_one(const BatchedCtx& c, const double (&a)
                         x = P(xmin - kGd * gmin);
                         const double sx2 = x - xm;
                         double q2[2] = {sx2 * sx2, sx2 * sy};
-                        cta64_sum<2>(q2, sm, par);
+                        bsum<2, NT>(q2, sm, par, s.own);
                         q[1] = q2[0]; q[2] = q2[1];
                     }
                 }
@@ -442,22 +456,25 @@ __device__ __forceinline__ void solve_one(const BatchedCtx& c, const double (&a)
     } else if constexpr (SOLVER == CCQP_SOLVER_SPG) {
         // solvers.py:906-975
         double x = s.x0;
-        double g = matvec(a, sm, xpar, s.act, x) + s.b; gemv++;
-        const double ag = matvec(a, sm, xpar, s.act, g); gemv++;
+        double g = matvec<NT>(a, sm, xpar, s.act, x) + s.b; gemv++;
+        const double ag = matvec<NT>(a, sm, xpar, s.act, g); gemv++;
         double q0[3] = {g * x, g * g, g * ag};
-        cta64_sum<3>(q0, sm, par);
+        bsum<3, NT>(q0, sm, par, s.own);
         double f = q0[0];
         double alpha = q0[1] / q0[2];
         mv = 2;
         SpgWindow<WREG> win;
         win.init(f);
         double dd_rep = NAN;
+        // the stream of uniforms lives in global memory: the sample of iteration k+1 is fetched while iteration k runs
+        // (an L2 round trip per iteration would otherwise sit on the dependent chain)
+        double u_next = (c.n_uniforms > 0) ? __ldg(uni) : 0.0;
         for (;;) {
             const double d = P(x - alpha * g) - x;
-            const double ad = matvec(a, sm, xpar, s.act, d); gemv++; mv++;
+            const double ad = matvec<NT>(a, sm, xpar, s.act, d); gemv++; mv++;
             if (mv >= maxmv) break;
             double q[3] = {d * d, d * ad, d * g};
-            cta64_sum<3>(q, sm, par);
+            bsum<3, NT>(q, sm, par, s.own);
             const double dd = q[0], dAd = q[1], dg = q[2];
             dd_rep = dd;
             if (dd <= c.thr_le) break;                                // sqrt(dd) <= tol (:949)
@@ -468,8 +485,9 @@ __device__ __forceinline__ void solve_one(const BatchedCtx& c, const double (&a)
             const double hi = (c.sig2 < bhat) ? c.sig2 : bhat;        // Python min(bhat, sig2)
             if (hi != hi) { status = CCQP_ERR_RANGE; break; }
             if (draws >= c.n_uniforms) { status = CCQP_ERR_UNIFORMS_EXHAUSTED; break; }
-            const double bk = c.sig1 + (hi - c.sig1) * uni[draws];
+            const double bk = c.sig1 + (hi - c.sig1) * u_next;
             draws++;
+            u_next = (draws < c.n_uniforms) ? __ldg(uni + draws) : 0.0;
             x += bk * d;
             g += bk * ad;
             f += bk * bk * dg + 0.5 * (bk * bk) * dAd;                // :963 as written
@@ -484,27 +502,27 @@ __device__ __forceinline__ void solve_one(const BatchedCtx& c, const double (&a)
         constexpr bool AR = SOLVER == CCQP_SOLVER_APGD_AR;
         double x = s.x0, y = s.x0, xp = s.x0, xhat = 1.0, axp = 0.0;
         const double d0 = s.act ? (s.x0 - 1.0) : 0.0;
-        const double ad0 = matvec(a, sm, xpar, s.act, d0); gemv++; mv = 1;
+        const double ad0 = matvec<NT>(a, sm, xpar, s.act, d0); gemv++; mv = 1;
         double q0[2] = {ad0 * ad0, d0 * d0};
-        cta64_sum<2>(q0, sm, par);
+        bsum<2, NT>(q0, sm, par, s.own);
         double L = sqrt(q0[0]) / sqrt(q0[1]);
         double t = 1.0 / L, theta = 1.0, resmin = INFINITY, res2 = NAN;
         for (;;) {
-            const double ay = matvec(a, sm, xpar, s.act, y); gemv++; mv++;
+            const double ay = matvec<NT>(a, sm, xpar, s.act, y); gemv++; mv++;
             if (mv >= maxmv) break;
             const double g = ay + s.b;
             xp = P(y - t * g);
             bool have12 = false;
             double rt1 = 0.0, rt2 = 0.0;
             for (;;) {
-                axp = matvec(a, sm, xpar, s.act, xp); gemv++; mv++;
+                axp = matvec<NT>(a, sm, xpar, s.act, xp); gemv++; mv++;
                 const bool lim = mv >= maxmv;
                 const double df = xp - y;
                 double qa[4] = {xp * axp, xp * s.b, g * df, df * df};
-                cta64_sum<4>(qa, sm, par);
+                bsum<4, NT>(qa, sm, par, s.own);
                 if (!have12) {       // the two outer sums (:285-286) ride along with the first inner reduction
                     double qb[2] = {y * ay, y * s.b};
-                    cta64_sum<2>(qb, sm, par);
+                    bsum<2, NT>(qb, sm, par, s.own);
                     rt1 = qb[0] * 0.5; rt2 = qb[1];
                     have12 = true;
                 }
@@ -518,8 +536,8 @@ __device__ __forceinline__ void solve_one(const BatchedCtx& c, const double (&a)
             const double beta = theta * (1 - theta) / (theta * theta + theta_n);
             double yn = (1 + beta) * xp - beta * x;
             double q[2] = {resid2(xp, axp + s.b), AR ? g * (xp - x) : 0.0};
-            if (AR) cta64_sum<2>(q, sm, par);
-            else { double q1[1] = {q[0]}; cta64_sum<1>(q1, sm, par); q[0] = q1[0]; }
+            if (AR) bsum<2, NT>(q, sm, par, s.own);
+            else { double q1[1] = {q[0]}; bsum<1, NT>(q1, sm, par, s.own); q[0] = q1[0]; }
             res2 = q[0];
             iters++;
             if (AR) { res = sqrt(res2); if (res < resmin) { resmin = res; xhat = xp; } }
@@ -538,44 +556,44 @@ __device__ __forceinline__ void solve_one(const BatchedCtx& c, const double (&a)
         // dense program (dense.cuh solve_mprgp) with one unknown per thread
         auto feas = [&](double v) { return is_close(v, clampd(v, s.lo, s.hi)); };
         double xk = clampd(s.x0, s.lo, s.hi), xn = xk;
-        double gk = matvec(a, sm, xpar, s.act, xk) + s.b, gn = gk; gemv++; mv = 1;
+        double gk = matvec<NT>(a, sm, xpar, s.act, xk) + s.b, gn = gk; gemv++; mv = 1;
         double r1[1] = {resid2(xk, gk)};
-        cta64_sum<1>(r1, sm, par);
+        bsum<1, NT>(r1, sm, par, s.own);
         double res2 = r1[0];
         if (!(res2 < c.thr_lt)) {
-            const double ag = matvec(a, sm, xpar, s.act, gk); gemv++; mv++;       // counted (:1077-1078)
+            const double ag = matvec<NT>(a, sm, xpar, s.act, gk); gemv++; mv++;       // counted (:1077-1078)
             double q2[2] = {gk * ag, gk * gk};
-            cta64_sum<2>(q2, sm, par);
+            bsum<2, NT>(q2, sm, par, s.own);
             double abb = q2[1] / q2[0];
             bool abb_lazy = false;                      // true: abb = BB(xk - xn) still to be evaluated
             double p = feas(xk) ? gk : 0.0, Ap = 0.0;
             for (;;) {
-                gk = matvec(a, sm, xpar, s.act, xk) + s.b; gemv++; mv++;
+                gk = matvec<NT>(a, sm, xpar, s.act, xk) + s.b; gemv++; mv++;
                 if (mv >= maxmv) break;
                 const bool cl = feas(xk);                                          // delta (:1093)
                 const double psi = cl ? gk : 0.0;
                 double q3[3] = {psi * psi, psi * p, (cl || !s.act) ? 0.0 : 1.0};
-                cta64_sum<3>(q3, sm, par);
+                bsum<3, NT>(q3, sm, par, s.own);
                 double betbet = 0.0;
                 if (q3[2] > 0.0) {
                     // some entry is not (close to) feasible: normal_vector of the Box (:306-322) and the GLOBAL n.g
                     const double px = clampd(xk, s.lo, s.hi), dx = xk - px;
                     double d1[1] = {dx * dx};
-                    cta64_sum<1>(d1, sm, par);
+                    bsum<1, NT>(d1, sm, par, s.own);
                     double nv = 0.0;
                     if (s.act && is_close(sqrt(d1[0]), 0.0)) nv = is_close(px, s.hi) ? 1.0 : (is_close(px, s.lo) ? -1.0 : 0.0);
                     double s1[1] = {nv * gk};
-                    cta64_sum<1>(s1, sm, par);
+                    bsum<1, NT>(s1, sm, par, s.own);
                     const double mng = s1[0] < 0.0 ? s1[0] : 0.0;                  // np.min([0, n.g])
                     const double bv = ((cl || !s.act) ? 0.0 : 1.0) * (gk - mng * nv);
                     double s2[1] = {bv * bv};
-                    cta64_sum<1>(s2, sm, par);
+                    bsum<1, NT>(s2, sm, par, s.own);
                     betbet = s2[0];
                 }
                 if (betbet < q3[0]) {
-                    Ap = matvec(a, sm, xpar, s.act, p); gemv++; mv++;
+                    Ap = matvec<NT>(a, sm, xpar, s.act, p); gemv++; mv++;
                     double s1[1] = {p * Ap};
-                    cta64_sum<1>(s1, sm, par);
+                    bsum<1, NT>(s1, sm, par, s.own);
                     if (mv >= maxmv) break;
                     const double pAp = s1[0];
                     const double acg = q3[1] / pAp;
@@ -586,7 +604,7 @@ __device__ __forceinline__ void solve_one(const BatchedCtx& c, const double (&a)
                             double al = af;
                             for (int j = 0; j < 64; ++j, al *= 0.5) if (!feas(xk - al * p)) m &= ~(1ull << j);
                         }
-                        m = cta64_and(m, sm, par);
+                        m = band<NT>(m, sm, par);
                         if (m) { const int j = __ffsll((long long)m) - 1; for (int q = 0; q < j; ++q) af *= 0.5; break; }
                         for (int q = 0; q < 64; ++q) af *= 0.5;
                         if (pass >= 20) break;
@@ -603,10 +621,10 @@ __device__ __forceinline__ void solve_one(const BatchedCtx& c, const double (&a)
                         const double xh = xk - af * p, gh = gk - af * Ap;
                         const double sx = xh - xk, sg = gh - gk;
                         double s2[2] = {sx * sx, sx * sg};
-                        cta64_sum<2>(s2, sm, par);
+                        bsum<2, NT>(s2, sm, par, s.own);
                         const double al = s2[0] / (s2[1] + 10 * kEps);
                         xn = clampd(xh - al * gh, s.lo, s.hi);
-                        gn = matvec(a, sm, xpar, s.act, xn) + s.b; gemv++; mv++;
+                        gn = matvec<NT>(a, sm, xpar, s.act, xn) + s.b; gemv++; mv++;
                         if (mv >= maxmv) break;
                         p = feas(xn) ? gn : 0.0;
                         abb_lazy = true;
@@ -614,9 +632,9 @@ __device__ __forceinline__ void solve_one(const BatchedCtx& c, const double (&a)
                 } else {                                                           // proportioning step :1164-1182
                     if (abb_lazy) {
                         const double w = xk - xn;
-                        const double Aw = matvec(a, sm, xpar, s.act, w); gemv++;  // not counted (:1129,:1163,:1172)
+                        const double Aw = matvec<NT>(a, sm, xpar, s.act, w); gemv++;  // not counted (:1129,:1163,:1172)
                         double s2[2] = {w * w, w * Aw};
-                        cta64_sum<2>(s2, sm, par);
+                        bsum<2, NT>(s2, sm, par, s.own);
                         abb = s2[0] / (s2[1] + 10 * kEps);
                     }
                     xn = clampd(xk - abb * gk, s.lo, s.hi);
@@ -626,7 +644,7 @@ __device__ __forceinline__ void solve_one(const BatchedCtx& c, const double (&a)
                     p = feas(xn) ? gn : 0.0;                                       // stale gn (:1181)
                 }
                 double r2[1] = {resid2(xn, gn)};
-                cta64_sum<1>(r2, sm, par);
+                bsum<1, NT>(r2, sm, par, s.own);
                 res2 = r2[0];
                 iters++;
                 if (res2 < c.thr_lt) break;
@@ -650,15 +668,23 @@ constexpr int batched_min_ctas(int solver) {
     return (solver == CCQP_SOLVER_PGD || solver == CCQP_SOLVER_BBPGD || solver == CCQP_SOLVER_SPG) ? CCQP_BATCHED_CTAS : 5;
 }
 
-template <int SOLVER, bool WREG, bool GEN>
-__global__ void __launch_bounds__(kBN, GEN ? 5 : batched_min_ctas(SOLVER)) batched_kernel(const BatchedCtx c) {
-    __shared__ __align__(16) BatchedSmem<GEN> sm;
+extern __shared__ __align__(16) unsigned char batched_dyn_smem[];       // NT = 256: the 141 KB of BatchedSmem are dynamic
+
+template <int SOLVER, bool WREG, bool GEN, int NT>
+__global__ void __launch_bounds__(NT, NT == 64 ? (GEN ? 5 : batched_min_ctas(SOLVER)) : 1) batched_kernel(const BatchedCtx c) {
+    using L = BL<NT>;
+    BatchedSmem<GEN, NT>* smp;
+    if constexpr (NT == 64) { __shared__ __align__(16) BatchedSmem<GEN, 64> sm_static; smp = &sm_static; }
+    else smp = reinterpret_cast<BatchedSmem<GEN, NT>*>(batched_dyn_smem);
+    BatchedSmem<GEN, NT>& sm = *smp;
     const int t = threadIdx.x, n = c.n;
-    const int cb = t & (kBRows - 1), row0 = kBRows * (t >> kBLog), col0 = kBCols * cb;
+    const int cb = t & (L::NB - 1), key = cb >> L::SH, row0 = kBRows * (t / L::NB), col0 = kBCols * cb;
+    const int u = row0 + key;               // the unknown this thread holds (NT = 64: u == t)
+    const bool primary = L::SH == 0 || !(t & 1);
     int par = 0, xpar = 0;
     BShared sh;
-    sh.xs_wr = smem_u32(&sm.xs[0][t + 2 * (t / kBCols)]);
-    sh.xs_rd = smem_u32(&sm.xs[0][kBSlice * cb]);
+    sh.xs_wr = smem_u32(&sm.xs[0][u + 2 * (u / kBCols)]);
+    sh.xs_rd = smem_u32(&sm.xs[0][L::SLICE * cb]);
     sh.red = smem_u32(&sm.red[0][0][0]);
     const size_t prob_elems = (size_t)n * n;
 
@@ -674,9 +700,9 @@ __global__ void __launch_bounds__(kBN, GEN ? 5 : batched_min_ctas(SOLVER)) batch
     if (t == 0) { mbar_init(&sm.mbar, 1); mbar_fence_init(); }
     auto issue_load = [&](int prob) {       // one 8n-byte bulk copy per row into the padded tile (+ 3 for the vectors), one mbarrier
         if (t == 0) mbar_expect_tx(&sm.mbar, (uint32_t)(prob_elems * 8) + (vstaged ? 3u * (uint32_t)(n * 8) : 0u));
-        if (t < n) bulk_g2s(sm.tile + t * kBPitch, c.A + (size_t)prob * prob_elems + (size_t)t * n, (uint32_t)(n * 8), &sm.mbar);
-        if (vstaged && t >= kBN - 3) {      // three otherwise idle-ish threads (the mbarrier's expect_tx is program-ordered only in thread 0,
-            const int w = t - (kBN - 3);    // but a complete_tx that arrives first just drives the pending count negative: legal)
+        if (t < n) bulk_g2s(sm.tile + t * L::PITCH, c.A + (size_t)prob * prob_elems + (size_t)t * n, (uint32_t)(n * 8), &sm.mbar);
+        if (vstaged && t >= NT - 3) {       // three otherwise idle-ish threads (the mbarrier's expect_tx is program-ordered only in thread 0,
+            const int w = t - (NT - 3);     // but a complete_tx that arrives first just drives the pending count negative: legal)
             const double* src = w == 0 ? c.b + (size_t)prob * n : (w == 1 ? c.lb : c.ub) + (size_t)prob * c.bound_stride;
             bulk_g2s(sm.vstage[w], src, (uint32_t)(n * 8), &sm.mbar);
         }
@@ -693,13 +719,15 @@ __global__ void __launch_bounds__(kBN, GEN ? 5 : batched_min_ctas(SOLVER)) batch
     if (staged && cur < c.batch) { fence_proxy_async(); issue_load(cur); }
 #endif
     while (cur < c.batch) {
-        // ---- register fill: this thread's sub-block; register row r <- row row0 + (r ^ cb) (see matvec)
+        // ---- register fill: this thread's sub-block; register row r <- row row0 + (r ^ key) (see matvec)
         double a[kBRows][kBCols];
         const double* Ap = c.A + (size_t)cur * prob_elems;
         BState s;
-        s.act = t < n;
-        const size_t vo = (size_t)cur * n + t;
-        const size_t bo = (size_t)cur * c.bound_stride + t;
+        s.u = u;
+        s.act = u < n;
+        s.own = s.act && primary;
+        const size_t vo = (size_t)cur * n + u;
+        const size_t bo = (size_t)cur * c.bound_stride + u;
         if (staged) {
 #if CCQP_BATCHED_STAGE
             mbar_wait(&sm.mbar, phase);
@@ -707,17 +735,17 @@ __global__ void __launch_bounds__(kBN, GEN ? 5 : batched_min_ctas(SOLVER)) batch
             const uint32_t tb = smem_u32(sm.tile);
 #pragma unroll
             for (int r = 0; r < kBRows; ++r) {
-                const int row = row0 + (r ^ cb);
+                const int row = row0 + (r ^ key);
 #pragma unroll
                 for (int j = 0; j < kBCols; j += 2) {
-                    if (row < n && col0 + j < n) lds_f64x2(tb + (uint32_t)(row * kBPitch + col0 + j) * 8u, a[r][j], a[r][j + 1]);
+                    if (row < n && col0 + j < n) lds_f64x2(tb + (uint32_t)(row * L::PITCH + col0 + j) * 8u, a[r][j], a[r][j + 1]);
                     else { a[r][j] = 0.0; a[r][j + 1] = 0.0; }
                 }
             }
             if (vstaged) {
-                s.b = s.act ? sm.vstage[0][t] : 0.0;
-                s.lo = s.act ? sm.vstage[1][t] : 0.0;
-                s.hi = s.act ? sm.vstage[2][t] : 0.0;
+                s.b = s.act ? sm.vstage[0][u] : 0.0;
+                s.lo = s.act ? sm.vstage[1][u] : 0.0;
+                s.hi = s.act ? sm.vstage[2][u] : 0.0;
             }
 #endif
         } else if (c.vec_ok) {
@@ -725,7 +753,7 @@ __global__ void __launch_bounds__(kBN, GEN ? 5 : batched_min_ctas(SOLVER)) batch
             for (int r = 0; r < kBRows; ++r) {
 #pragma unroll
                 for (int j = 0; j < kBCols; j += 4) {
-                    const int row = row0 + (r ^ cb);
+                    const int row = row0 + (r ^ key);
                     if (row < n && col0 + j < n) {
                         double v[4];
                         ldg256_stream<false>(Ap + (size_t)row * n + col0 + j, v);
@@ -738,7 +766,7 @@ __global__ void __launch_bounds__(kBN, GEN ? 5 : batched_min_ctas(SOLVER)) batch
             for (int r = 0; r < kBRows; ++r)
 #pragma unroll
                 for (int j = 0; j < kBCols; ++j)
-                    a[r][j] = (row0 + (r ^ cb) < n && col0 + j < n) ? ldg_stream(Ap + (size_t)(row0 + (r ^ cb)) * n + col0 + j) : 0.0;
+                    a[r][j] = (row0 + (r ^ key) < n && col0 + j < n) ? ldg_stream(Ap + (size_t)(row0 + (r ^ key)) * n + col0 + j) : 0.0;
         }
         if (!vstaged) {
             s.b = s.act ? c.b[vo] : 0.0;
@@ -746,9 +774,9 @@ __global__ void __launch_bounds__(kBN, GEN ? 5 : batched_min_ctas(SOLVER)) batch
             s.hi = s.act ? c.ub[bo] : 0.0;
         }
         if constexpr (GEN) {
-            s.kind = s.act ? c.ekind[t] : kIdentity;
-            s.boff = s.act ? c.eoff[t] : 0; s.bdim = s.act ? c.edim[t] : 0; s.bnk = s.act ? c.enk[t] : 0;
-            s.bpar = s.act ? c.epar[t] : 0.0;
+            s.kind = s.act ? c.ekind[u] : kIdentity;
+            s.boff = s.act ? c.eoff[u] : 0; s.bdim = s.act ? c.edim[u] : 0; s.bnk = s.act ? c.enk[u] : 0;
+            s.bpar = s.act ? c.epar[u] : 0.0;
             s.pj = smem_u32(&sm.pj[0][0]);
         }
         s.x0 = (s.act && c.x0) ? c.x0[vo] : 0.0;
@@ -761,15 +789,15 @@ __global__ void __launch_bounds__(kBN, GEN ? 5 : batched_min_ctas(SOLVER)) batch
             if (staged) { fence_proxy_async(); issue_load(nxt); } else
 #endif
             prefetch_l2(nxt);
-            if (c.x0 && s.act) asm volatile("prefetch.global.L2 [%0];" ::"l"(c.x0 + (size_t)nxt * n + t));
+            if (c.x0 && s.own) asm volatile("prefetch.global.L2 [%0];" ::"l"(c.x0 + (size_t)nxt * n + u));
             if (t == 0) after = atomicAdd(c.counter, 1u);     // consumed at the end of the solve
         } else if (t == 0) after = (unsigned)c.batch;
 
         double xsol = 0.0;
         BatchedOut o;
-        solve_one<SOLVER, WREG, GEN>(c, a, sh, s, c.uniforms ? c.uniforms + (size_t)cur * c.n_uniforms : nullptr, par, xpar,
+        solve_one<SOLVER, WREG, GEN, NT>(c, a, sh, s, c.uniforms ? c.uniforms + (size_t)cur * c.n_uniforms : nullptr, par, xpar,
                                      xsol, o);
-        if (s.act) c.x_out[vo] = xsol;
+        if (s.own) c.x_out[vo] = xsol;
         if (t == 0) { c.out[cur] = o; sm.next = (int)after; }   // everybody read the old value right after the barrier above
         cur = nxt;
     }
@@ -805,18 +833,28 @@ inline double sqrt_threshold(double tol, bool strict) {
     return out;
 }
 
-template <int SOLVER, bool WREG, bool GEN = false>
-inline cudaError_t launch_batched(const BatchedCtx& c, int sm_count, cudaStream_t stream) {
+template <int SOLVER, bool WREG, bool GEN, int NT>
+inline cudaError_t launch_batched_nt(const BatchedCtx& c, int sm_count, cudaStream_t stream) {
     int per_sm = 0;
-    cudaFuncSetAttribute(batched_kernel<SOLVER, WREG, GEN>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, batched_kernel<SOLVER, WREG, GEN>, kBN, 0);
+    const size_t dyn = NT == 64 ? 0 : sizeof(BatchedSmem<GEN, NT>);
+    auto kern = batched_kernel<SOLVER, WREG, GEN, NT>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaError_t e = dyn ? cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) : cudaSuccess;
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, dyn);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     if (const char* e = getenv("CCQP_BATCHED_CTAS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(e)));   // tuning hook
     long long grid = (long long)sm_count * per_sm;
     if (grid > c.batch) grid = c.batch;
-    batched_kernel<SOLVER, WREG, GEN><<<(unsigned)grid, kBN, 0, stream>>>(c);
+    kern<<<(unsigned)grid, NT, dyn, stream>>>(c);
     return cudaGetLastError();
+}
+// n <= 64: 64 threads per problem, A in 128 registers per thread, up to 6 problems per SM; 64 < n <= 128: 256 threads, one per SM
+template <int SOLVER, bool WREG, bool GEN = false>
+inline cudaError_t launch_batched(const BatchedCtx& c, int sm_count, cudaStream_t stream) {
+    return c.n <= kBN ? launch_batched_nt<SOLVER, WREG, GEN, 64>(c, sm_count, stream)
+                      : launch_batched_nt<SOLVER, WREG, GEN, 256>(c, sm_count, stream);
 }
 
 // One projection table shared by every problem of a batch (ccqp_solve_batched_table), per element, on the HOST
@@ -836,7 +874,7 @@ inline int batched_solve(cudaStream_t stream, int sm_count, const BatchedTable* 
                          int* launches, std::string& err, const std::function<void*(size_t)>& alloc) {
 #define BCU(call)                                                                                  \
     do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { err = std::string(#call) + ": " + cudaGetErrorString(e__); return CCQP_ERR_CUDA; } } while (0)
-    if (n > kBN) return CCQP_ERR_UNSUPPORTED;
+    if (n > kBNMax) return CCQP_ERR_UNSUPPORTED;
     if (tab && solver == CCQP_SOLVER_MPRGP) return CCQP_ERR_UNSUPPORTED;     // batched MPRGP: Box per problem only
     if (batch >= (1LL << 31) - 1024) return CCQP_ERR_INVALID_ARG;
     const bool host = memtype == CCQP_MEM_HOST;
@@ -845,7 +883,7 @@ inline int batched_solve(cudaStream_t stream, int sm_count, const BatchedTable* 
     const size_t szU = (solver == CCQP_SOLVER_SPG) ? (size_t)batch * n_uniforms * 8 : 0;
     const size_t szO = (size_t)batch * sizeof(BatchedOut);
     auto al = [](size_t v) { return (v + 255) / 256 * 256; };
-    size_t total = 256 + al(szO) + 8 * al((size_t)kBN * 8);
+    size_t total = 256 + al(szO) + 8 * al((size_t)kBNMax * 8);
     if (host) total += al(szA) + 4 * al(szV) + al(szV) + al(szU);
     unsigned char* ws = static_cast<unsigned char*>(alloc(total));
     if (!ws) { err = "workspace allocation failed"; return CCQP_ERR_CUDA; }
@@ -877,7 +915,7 @@ inline int batched_solve(cudaStream_t stream, int sm_count, const BatchedTable* 
     c.bound_stride = n;
     if (tab) {        // the shared table: seven small per-element arrays, uploaded once per call
         auto up = [&](const void* src, size_t bytes) -> void* {
-            void* d = take((size_t)kBN * 8);
+            void* d = take((size_t)kBNMax * 8);
             return cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, stream) == cudaSuccess ? d : nullptr;
         };
         c.lb = static_cast<const double*>(up(tab->lo.data(), (size_t)n * 8));

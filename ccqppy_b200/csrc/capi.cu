@@ -181,6 +181,9 @@ Tiling choose_tiling(const ccqp_handle* h) {
     if (h->d_val) {     // CSR: the two panel buffers together are the ring of TMA stages of the entry stream
         t.CW = kCsrCW; t.SW = kCsrCW; t.np = 1; t.nseg = 1; t.rows_max = kCsrRowsMax;   // (the psum region holds the row-pointer windows)
         t.smem = dense_smem_bytes(t.CW, t.rows_max, t.nseg);
+        // single-GPU and sharded solves run the many-warps build of the kernels (csr.cu), whose windows are larger;
+        // emulated ranks run this file's build (emu.cu), see launch_dense
+        if (!h->emulated) { t.rows_max = csr_variant_rows_max(); t.smem = csr_variant_smem(); }
         return t;
     }
     t.rows_max = (int)((nrows + t.grid - 1) / t.grid) + 1;
@@ -224,7 +227,8 @@ void fill_ctx(ccqp_handle* h, DenseCtx& c, const Tiling& t) {
         const double mean = h->d_val ? (double)h->nnz / (double)std::max<long long>(h->nrows, 1) : 0.0;
         // lanes that sum one row out of the shared-memory products: about 8-16 entries per lane
         // (a tile of 4096 entries should hold about as many rows as there are groups: one pass over the rows)
-        c.csr_group = mean >= 512 ? 32 : mean >= 256 ? 16 : mean >= 128 ? 8 : mean >= 64 ? 4 : mean >= 32 ? 2 : 1;
+        const double per_tile = (h->emulated ? kDenseThreads : csr_variant_threads()) * mean / kCsrTile;   // lanes per row of a tile
+        c.csr_group = per_tile >= 32 ? 32 : per_tile >= 16 ? 16 : per_tile >= 8 ? 8 : per_tile >= 4 ? 4 : per_tile >= 2 ? 2 : 1;
         c.csr_group = env_int("CCQP_CSR_GROUP", c.csr_group, ok_csr_group);
         c.csr_l1 = env_int("CCQP_CSR_L1", 1, ok_bool);
         c.csr_tma = ((reinterpret_cast<uintptr_t>(h->d_val) & 15) == 0 && (reinterpret_cast<uintptr_t>(h->d_idx) & 15) == 0) ? 1 : 0;
@@ -276,6 +280,13 @@ ccqp_status launch_dense(ccqp_handle* h, DenseCtx& c, const Tiling& t, bool coop
         h->smem_attr_mask |= 1u << op_slot(OP);
     }
     if (cooperative) CU(h, cudaMemsetAsync(h->flags.p, 0, kSyncBytes, h->stream));   // barrier counters
+    if (c.csr_val && !h->emulated) {        // operator-form Hessian: the many-warps build of the same kernels (csr.cu)
+        static_assert(sizeof(DenseCtx) % 8 == 0, "DenseCtx");
+        if (csr_variant_ctx_bytes() != sizeof(DenseCtx)) { h->last_error = "csr.cu was built from different headers"; return CCQP_ERR_CUDA; }
+        CU(h, csr_variant_launch(OP, &c, t.grid, t.smem, cooperative, h->stream));
+        h->launches += 1;
+        return CCQP_OK;
+    }
     void* args[] = {&c};
     if (cooperative)
         CU(h, cudaLaunchCooperativeKernel((const void*)dense_kernel<OP>, dim3(t.grid), dim3(kDenseThreads), args, t.smem, h->stream));

@@ -34,6 +34,9 @@ namespace ccqp {
 #ifndef CCQP_UNROLL
 #define CCQP_UNROLL 16
 #endif
+#ifndef CCQP_CSR_ONLY
+#define CCQP_CSR_ONLY 0       // 1: the dense mat-vec loop is compiled out (csr.cu: the many-warps build of the solver programs)
+#endif
 constexpr int kDenseThreads = CCQP_DENSE_THREADS;
 constexpr int kDenseWarps = kDenseThreads / 32;
 constexpr int kUnroll = CCQP_UNROLL;  // 256-bit loads in flight per lane
@@ -266,8 +269,9 @@ __device__ __forceinline__ double dot_seg_generic(const double* __restrict__ aro
 //   on the launch shape.  The stream's final tile, if its length is not a multiple of 4 entries (bulk copies move
 //   multiples of 16 bytes), is read with ordinary loads.
 // Algorithmic HBM bytes per mat-vec: 12 per stored entry + 8 (rows + 1) + the vectors.
-constexpr int kCsrE = 16;
-constexpr int kCsrTile = kDenseThreads * kCsrE;
+constexpr int kCsrTile = 4096;                       // independent of the launch shape (csr_tile_row is built for it)
+constexpr int kCsrE = kCsrTile / kDenseThreads;      // entries per thread per tile: 16 at 256 threads, 4 at 1024
+static_assert(kCsrE * kDenseThreads == kCsrTile && kCsrE >= 1, "threads per CTA must divide the CSR tile");
 constexpr int kCsrStages = 4;
 constexpr int kCsrStageBytes = kCsrTile * 12;         // values, then column ids
 constexpr int kCsrCW = kCsrStages * kCsrStageBytes / 16;   // "panel width" that makes the two panel buffers hold the ring
@@ -285,21 +289,31 @@ template <class Epi>
 __device__ __forceinline__ void gemv_phase_csr(Kst& k, const DenseCtx& c, const double* v, Epi epi) {
     const int tid = threadIdx.x;
     const int G = c.csr_group, glane = tid & (G - 1), gid = tid / G, ngroups = kDenseThreads / G;
+    const int warp_gid0 = (tid & ~31) / G;                           // first group of this warp
     const int cr0 = k.r0 - c.row0, cr1 = k.r1 - c.row0;               // this CTA's rows, relative to the shard
     volatile double* carry_slot = k.sm.scratch;                       // [2], by tile parity
-    long long* win = reinterpret_cast<long long*>(k.sm.psum);         // [2][kCsrWin], by tile parity
+    int4* dsc = reinterpret_cast<int4*>(k.sm.scratch + 4);            // [kCsrStages][2]: per-tile descriptors, written by thread 0
+    int* win = reinterpret_cast<int*>(k.sm.psum);                     // [2][kCsrWin], by tile parity: tile-relative row pointers
     unsigned char* ring = reinterpret_cast<unsigned char*>(k.sm.vbuf[0]);
     const long long P0 = cr1 > cr0 ? c.csr_ptr[cr0] : 0, P1 = cr1 > cr0 ? c.csr_ptr[cr1] : 0;
     if (P1 > P0) {                                                    // CTA-uniform
-        const long long nnz = c.csr_ptr[c.nrows];
         const long long g0 = P0 / kCsrTile;
         const int nt = (int)((P1 - 1) / kCsrTile - g0) + 1;
-        auto tile_count = [&](int t) { const long long T = (g0 + t) * kCsrTile; return (int)(nnz - T < kCsrTile ? nnz - T : kCsrTile); };
+        // Thread 0 describes a tile ONCE for everybody when it starts the tile's copies: {first row (open since the previous
+        // tile, or the CTA's first), rows, this CTA's entry range [lo, hi) inside the tile}, {entries, slow path}.  All positions
+        // inside a tile are 32-bit and tile-relative from here on: the 64-bit row pointers are touched once per row.
         auto issue = [&](int t) {                                     // thread 0 only
-            const int cnt = tile_count(t);
-            if ((cnt & 3) || !c.csr_tma) return;                      // ragged final tile of the stream: ordinary loads at consume time
-            const int st = t % kCsrStages;
+            const long long nnz = c.csr_ptr[c.nrows];
             const long long T = (g0 + t) * kCsrTile;
+            const int cnt = (int)(nnz - T < kCsrTile ? nnz - T : kCsrTile);
+            const int slow = ((cnt & 3) || !c.csr_tma) ? 1 : 0;       // ragged final tile of the stream / unaligned arrays: ordinary loads
+            int r_cur = t == 0 ? cr0 : c.csr_tile_row[g0 + t], r_last = c.csr_tile_row[g0 + t + 1];
+            if (r_last > cr1 - 1 || T + cnt >= P1) r_last = cr1 - 1;
+            const int lo = (int)((T > P0 ? T : P0) - T), hi = (int)((T + cnt < P1 ? T + cnt : P1) - T);
+            const int st = t % kCsrStages;
+            dsc[2 * st] = make_int4(r_cur, r_last - r_cur + 1, lo, hi);
+            dsc[2 * st + 1] = make_int4(cnt, slow, 0, 0);
+            if (slow) return;
             unsigned char* dst = ring + (size_t)st * kCsrStageBytes;
             mbar_expect_tx(&k.sm.mbar[st], (uint32_t)cnt * 12u);
             bulk_g2s_evict_first(dst, c.csr_val + T, (uint32_t)cnt * 8u, &k.sm.mbar[st]);
@@ -310,95 +324,94 @@ __device__ __forceinline__ void gemv_phase_csr(Kst& k, const DenseCtx& c, const 
             fence_proxy_async();
             for (int t = 0; t < nt && t < kCsrStages; ++t) issue(t);
         }
-        // Software pipeline over the tiles: the gather of tile t+1 is IN FLIGHT (16 loads per thread, in registers)
+        __syncthreads();                                              // descriptors of the first tiles are visible
+        // Software pipeline over the tiles: the gather of tile t+1 is IN FLIGHT (kCsrE loads per thread, in registers)
         // while the rows of tile t are summed; then the products of t+1 are formed and ONE barrier closes the step.
+        struct Tile { int r_cur, nrows, lo, hi, cnt, slow; };
+        auto describe = [&](int t) {
+            const int4 d0 = dsc[2 * (t % kCsrStages)], d1 = dsc[2 * (t % kCsrStages) + 1];
+            Tile d; d.r_cur = d0.x; d.nrows = d0.y; d.lo = d0.z; d.hi = d0.w; d.cnt = d1.x; d.slow = d1.y;
+            return d;
+        };
+        // pointer of row r as a position inside the tile that starts at T, clamped to [lo, hi + 1] (hi + 1 = "beyond this CTA's part")
+        auto rel = [&](long long p, long long T, const Tile& d) { p -= T; return p < d.lo ? d.lo : (p > d.hi ? d.hi + 1 : (int)p); };
         int j[kCsrE];
         double x[kCsrE];
-        long long pv = 0, pv_last = 0;
-        auto tile_rows = [&](int t, int& r_cur, int& r_last) {        // rows r_cur (open since tile t-1, or the CTA's first) .. r_last
-            const long long T = (g0 + t) * kCsrTile;
-            r_cur = t == 0 ? cr0 : c.csr_tile_row[g0 + t];
-            r_last = c.csr_tile_row[g0 + t + 1];
-            if (r_last > cr1 - 1 || T + tile_count(t) >= P1) r_last = cr1 - 1;
-        };
-        auto slow_tile = [&](int t) { return (tile_count(t) & 3) || !c.csr_tma; };     // CTA-uniform
-        auto gather_issue = [&](int t) {
+        int wv = 0;
+        auto gather_issue = [&](int t, const Tile& d) {
             const int st = t % kCsrStages;
-            int r_cur, r_last;
-            tile_rows(t, r_cur, r_last);
-            // row pointers r_cur .. r_cur + 256 of the tile -> shared window (stored by finish_products): one coalesced load
-            pv = r_cur + tid <= cr1 ? c.csr_ptr[r_cur + tid] : 0;
-            pv_last = (tid == 0 && r_cur + kDenseThreads <= cr1) ? c.csr_ptr[r_cur + kDenseThreads] : 0;
-            if (slow_tile(t)) return;
-            const int cnt = tile_count(t);
+            // row pointers of the tile's rows -> shared window (stored by finish_products): one coalesced load by as many threads as rows
+            if (tid <= d.nrows && tid < kCsrWin) wv = rel(c.csr_ptr[d.r_cur + tid], (g0 + t) * kCsrTile, d);
+            if (d.slow) return;
             const int* idx = reinterpret_cast<const int*>(ring + (size_t)st * kCsrStageBytes + kCsrTile * 8);
             mbar_wait(&k.sm.mbar[st], k.par[st]);
             k.par[st] ^= 1u;
+            if (d.cnt == kCsrTile) {
 #pragma unroll
-            for (int u = 0; u < kCsrE; ++u) { const int q = u * kDenseThreads + tid; j[u] = q < cnt ? idx[q] : 0; }
+                for (int u = 0; u < kCsrE; ++u) j[u] = idx[u * kDenseThreads + tid];
+            } else {
+#pragma unroll
+                for (int u = 0; u < kCsrE; ++u) { const int q = u * kDenseThreads + tid; j[u] = q < d.cnt ? idx[q] : 0; }
+            }
 #pragma unroll
             for (int u = 0; u < kCsrE; ++u) x[u] = c.csr_l1 ? ld_ca(v + j[u]) : ld_cg(v + j[u]);
         };
-        auto finish_products = [&](int t) {
+        auto finish_products = [&](int t, const Tile& d) {
             const int st = t % kCsrStages;
-            const long long T = (g0 + t) * kCsrTile;
-            const int cnt = tile_count(t);
             double* prod = reinterpret_cast<double*>(ring + (size_t)st * kCsrStageBytes);
-            long long* pw = win + (t & 1) * kCsrWin;
-            pw[tid] = pv;
-            if (tid == 0) pw[kDenseThreads] = pv_last;
-            if (slow_tile(t)) {                                       // ragged final tile of the stream / unaligned arrays
-                for (int q = tid; q < cnt; q += kDenseThreads) {
+            if (tid <= d.nrows && tid < kCsrWin) win[(t & 1) * kCsrWin + tid] = wv;
+            if (d.slow) {
+                const long long T = (g0 + t) * kCsrTile;
+                for (int q = tid; q < d.cnt; q += kDenseThreads) {
                     const double xv = c.csr_l1 ? ld_ca(v + __ldg(c.csr_idx + T + q)) : ld_cg(v + __ldg(c.csr_idx + T + q));
                     prod[q] = ldg_stream(c.csr_val + T + q) * xv;
                 }
+            } else if (d.cnt == kCsrTile) {
+#pragma unroll
+                for (int u = 0; u < kCsrE; ++u) prod[u * kDenseThreads + tid] *= x[u];
             } else {
 #pragma unroll
-                for (int u = 0; u < kCsrE; ++u) { const int q = u * kDenseThreads + tid; if (q < cnt) prod[q] *= x[u]; }
+                for (int u = 0; u < kCsrE; ++u) { const int q = u * kDenseThreads + tid; if (q < d.cnt) prod[q] *= x[u]; }
             }
         };
-        gather_issue(0);
-        finish_products(0);
+        Tile cur = describe(0);
+        gather_issue(0, cur);
+        finish_products(0, cur);
         __syncthreads();
         for (int t = 0; t < nt; ++t) {
             const int st = t % kCsrStages;
-            const long long T = (g0 + t) * kCsrTile;
-            const int cnt = tile_count(t);
-            const long long t0 = T > P0 ? T : P0, t1 = T + cnt < P1 ? T + cnt : P1;     // this CTA's entries of the tile
-            int r_cur, r_last;
-            tile_rows(t, r_cur, r_last);
-            const int nrows_t = r_last - r_cur + 1;
-            const long long* pw = win + (t & 1) * kCsrWin;
+            const int* pw = win + (t & 1) * kCsrWin;
             const double* prod = reinterpret_cast<const double*>(ring + (size_t)st * kCsrStageBytes);
-            // everybody is behind the barrier that ended step t-1: the stage of tile t-1 is free
+            // everybody is behind the barrier that ended step t-1: the stage (and the descriptor) of tile t-1 are free
             if (tid == 0 && t >= 1 && t - 1 + kCsrStages < nt) { fence_proxy_async(); issue(t - 1 + kCsrStages); }
-            if (t + 1 < nt) gather_issue(t + 1);
+            Tile nxt = cur;
+            if (t + 1 < nt) { nxt = describe(t + 1); gather_issue(t + 1, nxt); }
             const double carry_in = carry_slot[t & 1];
-            for (int kk = 0; kk * ngroups < nrows_t; ++kk) {          // CTA-uniform trip count
-                const int i = gid + kk * ngroups, r = r_cur + i;
-                const bool active = i < nrows_t;
-                long long p0 = 0, p1 = 0;
+            for (int kk = 0; kk * ngroups < cur.nrows; ++kk) {        // CTA-uniform trip count
+                if (warp_gid0 + kk * ngroups >= cur.nrows) continue;  // warp-uniform: nothing for this warp in this pass
+                const int i = gid + kk * ngroups, r = cur.r_cur + i;
+                const bool active = i < cur.nrows;
+                int p0 = cur.hi, p1 = cur.hi;
                 if (active) {
                     if (i + 1 < kCsrWin) { p0 = pw[i]; p1 = pw[i + 1]; }
-                    else { p0 = c.csr_ptr[r]; p1 = c.csr_ptr[r + 1]; }
+                    else { const long long T = (g0 + t) * kCsrTile; p0 = rel(c.csr_ptr[r], T, cur); p1 = rel(c.csr_ptr[r + 1], T, cur); }
                 }
-                const bool complete = active && p1 <= t1;            // the row ends inside this tile
+                const bool complete = active && p1 <= cur.hi;         // the row ends inside this CTA's part of the tile
+                const int hi = p1 < cur.hi ? p1 : cur.hi;
                 double a0 = 0.0, a1 = 0.0;
-                if (active) {
-                    const int lo = (int)((p0 > t0 ? p0 : t0) - T), hi = (int)((p1 < t1 ? p1 : t1) - T);
-                    int q = lo + glane;
-                    for (; q + G < hi; q += 2 * G) { a0 += prod[q]; a1 += prod[q + G]; }
-                    if (q < hi) a0 += prod[q];
-                }
+                int q = (p0 < cur.hi ? p0 : cur.hi) + glane;
+                for (; q + G < hi; q += 2 * G) { a0 += prod[q]; a1 += prod[q + G]; }
+                if (q < hi) a0 += prod[q];
                 double acc = a0 + a1;
                 for (int o = G >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
                 if (glane == 0 && active) {
                     if (i == 0) acc = carry_in + acc;                 // earlier tiles' part of the row first
                     if (complete) epi(c.row0 + r, acc);
-                    else carry_slot[(t + 1) & 1] = acc;               // the one row that continues into the next tile (r_last)
+                    else carry_slot[(t + 1) & 1] = acc;               // the one row that continues into the next tile (the last one)
                 }
             }
-            if (t + 1 < nt) finish_products(t + 1);
+            if (t + 1 < nt) finish_products(t + 1, nxt);
+            cur = nxt;
             __syncthreads();          // products + row-pointer window of tile t+1 and the carry of tile t are visible;
                                       // everybody has finished tile t
         }
@@ -413,7 +426,7 @@ __device__ __forceinline__ void gemv_phase_csr(Kst& k, const DenseCtx& c, const 
 // v: full-length global vector (npad entries, zero tail), complete before the phase starts.
 template <class Epi>
 __device__ __forceinline__ void gemv_phase(Kst& k, const DenseCtx& c, const double* v, Epi epi) {
-    if (c.csr_val) { gemv_phase_csr(k, c, v, epi); return; }
+    if (CCQP_CSR_ONLY || c.csr_val) { gemv_phase_csr(k, c, v, epi); return; }
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = c.n, CW = c.CW, SW = c.SW, np = c.np, nseg = c.nseg;
     const int nrows_cta = k.r1 - k.r0;
@@ -641,6 +654,7 @@ static __device__ void solve_spg(Kst& k, const DenseCtx& c) {
     double bk = 0.0;                     // pending update x += bk d, g += bk Ad (applied lazily)
     const double* Ad = c.vec[3];         // all zeros; multiplied by bk == 0 in the first pass
     int status = 0;
+    double u_next = c.n_uniforms > 0 ? c.uniforms[0] : 0.0;   // the sample of iteration k+1 is fetched during iteration k
     for (;;) {
         dbg_stamp(c, k.iters, 0);
         double s2[2] = {0.0, 0.0};       // d.d, d.g
@@ -684,8 +698,9 @@ static __device__ void solve_spg(Kst& k, const DenseCtx& c) {
         const double hi = (c.sig2 < bhat) ? c.sig2 : bhat;
         if (hi != hi) { status = 8; break; }                       // CCQP_ERR_RANGE
         if (k.draws >= c.n_uniforms) { status = 7; break; }        // CCQP_ERR_UNIFORMS_EXHAUSTED
-        const double u = c.uniforms[k.draws];
+        const double u = u_next;
         k.draws += 1;
+        u_next = k.draws < c.n_uniforms ? c.uniforms[k.draws] : 0.0;
         bk = c.sig1 + (hi - c.sig1) * u;
         f += bk * bk * dg + 0.5 * (bk * bk) * dAd;                  // :963 as written
         if (wcount < c.m) { window[wcount++] = f; }

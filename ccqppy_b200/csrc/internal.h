@@ -30,4 +30,12 @@ int batched_solve_table_entry(cudaStream_t stream, int sm_count, int solver, con
 // emu.cu -- one cooperative launch of dense_kernel_emu<solver> over world * G CTAs
 cudaError_t launch_dense_emu(int solver, const DenseCtx* d_ctxs, int world, int G, size_t smem, cudaStream_t stream);
 
+// csr.cu -- the solver kernels compiled for CSR Hessians (many warps per SM, dense mat-vec loop compiled out); `ctx` points
+// at a DenseCtx, `op` is a DenseOp.  csr_variant_smem(): dynamic shared memory of that build's CSR tiling.
+int csr_variant_threads();
+size_t csr_variant_smem();
+int csr_variant_rows_max();
+size_t csr_variant_ctx_bytes();
+cudaError_t csr_variant_launch(int op, const void* ctx, int grid, size_t smem, bool cooperative, cudaStream_t stream);
+
 }  // namespace ccqp

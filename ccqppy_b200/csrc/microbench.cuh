@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(64) probe_kernel(long long* cycles, double* si
     PROBE(PROBE_SQRT, v = sqrt(v) + 2.0)
     {
         const uint32_t base = smem_u32(sh);
-        double a, b;
+        double a, b = 0.0;
         PROBE(PROBE_LDS128_BCAST, { const uint32_t ad = base + ((__double2loint(v) & 1) << 4);
                                      asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(a), "=d"(b) : "r"(ad) : "memory"); v += a; })
         PROBE(PROBE_LDS128_DISTINCT, { const uint32_t ad = base + (((t & 31) + (__double2loint(v) & 1)) << 4);
@@ -92,10 +92,10 @@ __global__ void __launch_bounds__(64) probe_kernel(long long* cycles, double* si
     {
         double d[8][2];
         PROBE(PROBE_DMMA_X8, {
-#pragma unroll
+_Pragma("unroll")
             for (int u = 0; u < 8; ++u) dmma884(d[u][0], d[u][1], 0.25, v + u, 0.0, 0.0);
             v = d[0][0] * 1e-3;
-#pragma unroll
+_Pragma("unroll")
             for (int u = 1; u < 8; ++u) v += d[u][1] * 1e-9;
         })
     }
@@ -110,10 +110,10 @@ __global__ void __launch_bounds__(64) probe_kernel(long long* cycles, double* si
 #pragma unroll
         for (int u = 0; u < 8; ++u) f[u] = v + u;
         PROBE(PROBE_DMMA_X8_DFMA_X8, {          // do DMMA and DFMA share an issue path?  8 + 8 independent per trip
-#pragma unroll
+_Pragma("unroll")
             for (int u = 0; u < 8; ++u) { dmma884(d[u][0], d[u][1], 0.25, f[u], 0.0, 0.0); f[u] = fma(f[u], w, w); }
             v = d[0][0] * 1e-3;
-#pragma unroll
+_Pragma("unroll")
             for (int u = 1; u < 8; ++u) v += d[u][1] * 1e-9;
             f[0] += v * 1e-9;
         })

@@ -13,7 +13,7 @@ the host.
 
 Extensions beyond the reference API (all optional):
   * `solve(..., uniforms=...)`      explicit U[0,1) stream for SPG instead of the global NumPy RNG
-  * `solve_batched(A, b, lb, ub)`   many small box-QPs in one persistent kernel (n <= 64)
+  * `solve_batched(A, b, lb, ub)`   many small QPs in one persistent kernel (n <= 128; per-problem boxes or one shared table)
   * `solution_gpu_time`, `solution_hbm_bytes`, `solution_gemv_count` after a solve
   * A / b / x0 may be torch tensors; a CUDA tensor A is used in place (no copy)
 """

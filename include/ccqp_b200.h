@@ -175,7 +175,8 @@ ccqp_status ccqp_solve_wait(ccqp_handle* h, ccqp_result* result);
  *     CCQPSolverX(tol,max_mv).solve(A[i], b[i], x0[i], BoxProjOp(n, lb[i], ub[i]))
  * (solvers.py:94.. with solution_spaces.py:280).  A is [batch][n][n]; b, x0 (nullable), lb, ub,
  * x_out are [batch][n]; uniforms is [batch][n_uniforms] (SPG); results is [batch] in HOST memory.
- * Supported n: 1..64 (n = 64 is the tuned case); all seven solvers. */
+ * Supported n: 1..128; all seven solvers.  n <= 64 (the tuned case): 64 threads per problem, up to 6 problems in flight per SM;
+ * 64 < n <= 128: 256 threads per problem, one problem per SM; larger n: CCQP_ERR_UNSUPPORTED (use ccqp_solve). */
 ccqp_status ccqp_solve_batched(ccqp_handle* h, int solver, const ccqp_params* params, int64_t batch,
                                int64_t n, const double* A, const double* b, const double* x0,
                                const double* lb, const double* ub, const double* uniforms,

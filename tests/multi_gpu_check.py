@@ -30,7 +30,8 @@ def main():
     report, ok = [], True
     cases = [("tiny", pr.box_table(40), 40, 1.0),      # one CTA per rank: local syncs are plain barriers, cross syncs are not
              ("mixed", pr.mixed_table(1200), 1200, 1.0), ("box", pr.box_table(4096), 4096, 1.0),
-             ("sphere3", pr.sphere3_table(1000), 1000, 1.0), ("box_odd", pr.box_table(1023), 1023, 0.3)]
+             ("sphere3", pr.sphere3_table(1000), 1000, 1.0), ("box_odd", pr.box_table(1023), 1023, 0.3),
+             ("box_uneven", pr.box_table(3050), 3050, 1.0)]   # 3050 rows over 8 ranks: shards of 381 / 382 rows, one grid
     for tname, tab, n, mu in cases:
         A, b = pr.shift_problem(n, 5, mu)
         step = 1.0 / np.abs(A).sum(axis=1).max()

@@ -200,3 +200,47 @@ def test_batched_shared_table_errors_and_device():
     # every disc constraint holds
     x = np.asarray(h.solution).reshape(batch, 4, 3)
     assert (np.linalg.norm(x, axis=2) <= 0.5 * (1 + 1e-12)).all()
+
+
+@pytest.mark.parametrize("solver", [pr.PGD, pr.APGD, pr.APGD_AR, pr.BBPGD, pr.BBPGDF, pr.SPG, pr.MPRGP])
+@pytest.mark.parametrize("n", [128, 96, 65])
+def test_batched_n_up_to_128_matches_oracle(solver, n):
+    """64 < n <= 128: the 256-thread layout of the batched kernel (16 x 16 grid of 8 x 8 register blocks, two lanes per
+    unknown), problem by problem against the oracle."""
+    batch, max_mv, step, K = 20, 5000, 0.1, 512
+    if solver == pr.MPRGP:
+        batch = 6
+    tol = 1e-6 if solver in (pr.APGD, pr.APGD_AR) else 1e-8
+    A, b, lb, ub = make_batch(batch, n, seed0=300)
+    x0 = None if n != 96 else 0.5 * np.random.default_rng(4).standard_normal((batch, n))
+    s = make_solver(solver, tol, max_mv, step)
+    s.solve_batched(A, b, lb, ub, x0=x0, seeds=np.arange(batch), n_uniforms=K)
+    same = 0
+    for i in range(batch):
+        o = oracle_one(solver, A[i], b[i], lb[i], ub[i], None if x0 is None else x0[i], tol, max_mv, step, i, K)
+        assert bool(s.solution_converged[i]) == o["converged"]
+        mv = int(s.solution_num_matrix_vector_multiplications[i])
+        scale = max(np.linalg.norm(o["solution"]), 1e-300)
+        if mv == o["mv"]:
+            same += 1
+            assert np.linalg.norm(s.solution[i] - o["solution"]) <= 1e-9 * scale
+        else:
+            assert abs(mv - o["mv"]) <= max(2, round(0.1 * o["mv"])), (i, mv, o["mv"])
+            assert np.linalg.norm(s.solution[i] - o["solution"]) <= 1e-5 * scale
+    assert same >= 0.9 * batch, (same, batch)
+
+
+def test_batched_n128_shared_table_and_limit():
+    from helpers import op_from_table
+    from ccqppy_b200 import _capi
+    n, batch = 126, 12
+    tab = pr.sphere3_table(n, 0.4)
+    A = np.stack([pr.shift_problem(n, 900 + i)[0] for i in range(batch)])
+    b = np.stack([pr.shift_problem(n, 900 + i)[1] for i in range(batch)])
+    s = make_solver(pr.BBPGD, 1e-8, 5000).solve_batched(A, b, convex_proj_op=op_from_table(tab))
+    for i in range(batch):
+        o = orc.solve(pr.BBPGD, A[i], b[i], blocks=tab.blocks, params=tab.params, tol=1e-8, max_mv=5000)
+        assert int(s.solution_num_matrix_vector_multiplications[i]) == o["mv"]
+        assert np.linalg.norm(s.solution[i] - o["solution"]) <= 1e-9 * np.linalg.norm(o["solution"])
+    with pytest.raises(_capi.CCQPError):            # beyond the batched mode: use solve()
+        make_solver(pr.BBPGD, 1e-8, 100).solve_batched(np.zeros((2, 129, 129)), np.zeros((2, 129)), np.zeros((2, 129)), np.ones((2, 129)))

@@ -46,10 +46,10 @@ def test_status_codes_of_the_c_abi():
     assert lib.ccqp_set_matrix(h.h, P(A_shard), n, n, 0, 4, _capi.MEM_HOST) == 0
     assert solve() == 4                                                   # CCQP_ERR_UNSUPPORTED: a row shard needs ccqp_comm_attach
     assert lib.ccqp_status_string(4) == b"unsupported request" and lib.ccqp_status_string(99) == b"unknown status"
-    big = np.zeros((3, 65, 65))
-    v = np.zeros((3, 65))
-    assert lib.ccqp_solve_batched(h.h, _capi.BBPGD, ctypes.byref(prm), 3, 65, P(big), P(v), None, P(v), P(v), None, 0, P(v),
-                                  _capi.MEM_HOST, None, None) == 4        # n > 64
+    big = np.zeros((3, 129, 129))
+    v = np.zeros((3, 129))
+    assert lib.ccqp_solve_batched(h.h, _capi.BBPGD, ctypes.byref(prm), 3, 129, P(big), P(v), None, P(v), P(v), None, 0, P(v),
+                                  _capi.MEM_HOST, None, None) == 4        # n > 128
     assert lib.ccqp_solve_batched(h.h, 7, ctypes.byref(prm), 3, 8, P(big), P(v), None, P(v), P(v), None, 0, P(v),
                                   _capi.MEM_HOST, None, None) == 1        # unknown solver
     h.close()
