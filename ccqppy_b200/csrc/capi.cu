@@ -13,6 +13,7 @@
 #include <string>
 #include <vector>
 
+#define CCQP_DENSE_ONLY 1      // CSR Hessians run csr.cu's build of the kernels (emulated ranks: emu.cu's)
 #include "dense.cuh"
 #include "internal.h"
 #include "microbench.cuh"
@@ -122,7 +123,7 @@ ccqp_status copy_out(ccqp_handle* h, double* dst, const double* src, long long c
 }
 
 // slots of the work buffer (each npad doubles)
-enum { W_B = 0, W_X0, W_XOUT, W_HIN, W_HOUT, W_VEC0, W_COUNT = W_VEC0 + kNumVec };
+enum { W_B = 0, W_X0, W_XOUT, W_HIN, W_HOUT, W_YTMP, W_VEC0, W_COUNT = W_VEC0 + kNumVec };
 
 // The work buffer has the layout of the multi-GPU symmetric buffer (common.cuh kSym*Off): flags,
 // scalar exchange slots, then the work vectors.  Single GPU: a private allocation.  Sharded: the
@@ -237,6 +238,7 @@ void fill_ctx(ccqp_handle* h, DenseCtx& c, const Tiling& t) {
     }
     c.b = w + W_B * h->npad; c.x0 = w + W_X0 * h->npad; c.x_out = w + W_XOUT * h->npad;
     c.hook_in = w + W_HIN * h->npad; c.hook_out = w + W_HOUT * h->npad;
+    c.ytmp = w + W_YTMP * h->npad;
     for (int i = 0; i < kNumVec; ++i) c.vec[i] = w + (W_VEC0 + i) * h->npad;
     c.T.n = (int)h->n;
     c.T.lo = h->lo.as<double>(); c.T.hi = h->hi.as<double>(); c.T.ekind = h->ekind.as<uint8_t>();
@@ -252,6 +254,7 @@ void fill_ctx(ccqp_handle* h, DenseCtx& c, const Tiling& t) {
     c.gs.abort = reinterpret_cast<unsigned*>(h->flags.as<char>() + kSyncAbortOff);
     c.gs.go = reinterpret_cast<unsigned*>(h->flags.as<char>() + kSyncGoOff);
     c.gs.result = reinterpret_cast<unsigned long long*>(h->flags.as<char>() + kSyncResultOff);
+    c.gs.closerless = env_int("CCQP_SYNC_CLOSERLESS", 1, ok_bool);
     c.x.world = h->world; c.x.rank = h->rank;
     for (int s = 0; s < kMaxWorld; ++s) c.x.base[s] = (s < h->world) ? h->peer_base[s] : nullptr;
     if (h->world == 1) c.x.base[0] = h->work.as<char>();
@@ -280,7 +283,11 @@ ccqp_status launch_dense(ccqp_handle* h, DenseCtx& c, const Tiling& t, bool coop
         h->smem_attr_mask |= 1u << op_slot(OP);
     }
     if (cooperative) CU(h, cudaMemsetAsync(h->flags.p, 0, kSyncBytes, h->stream));   // barrier counters
-    if (c.csr_val && !h->emulated) {        // operator-form Hessian: the many-warps build of the same kernels (csr.cu)
+    if (c.csr_val && h->emulated) {
+        h->last_error = "the unit-test hooks of an emulated rank do not take a CSR matrix";
+        return CCQP_ERR_UNSUPPORTED;
+    }
+    if (c.csr_val) {        // operator-form Hessian: the many-warps build of the same kernels (csr.cu)
         static_assert(sizeof(DenseCtx) % 8 == 0, "DenseCtx");
         if (csr_variant_ctx_bytes() != sizeof(DenseCtx)) { h->last_error = "csr.cu was built from different headers"; return CCQP_ERR_CUDA; }
         CU(h, csr_variant_launch(OP, &c, t.grid, t.smem, cooperative, h->stream));

@@ -37,6 +37,9 @@ namespace ccqp {
 #ifndef CCQP_CSR_ONLY
 #define CCQP_CSR_ONLY 0       // 1: the dense mat-vec loop is compiled out (csr.cu: the many-warps build of the solver programs)
 #endif
+#ifndef CCQP_DENSE_ONLY
+#define CCQP_DENSE_ONLY 0     // 1: the CSR mat-vec phase is compiled out (capi.cu: the product's dense kernels carry no CSR code --
+#endif                        //    the register allocation and the schedule of the dense loop depend on everything inlined next to it)
 constexpr int kDenseThreads = CCQP_DENSE_THREADS;
 constexpr int kDenseWarps = kDenseThreads / 32;
 constexpr int kUnroll = CCQP_UNROLL;  // 256-bit loads in flight per lane
@@ -94,6 +97,7 @@ struct DenseCtx {
     // test hooks
     const double* hook_in;
     double* hook_out;
+    double* ytmp;       // [nrows] CSR phase: row sums of this rank's rows, handed from the tile loop to the epilogue pass
     long long* dbg;     // phase time stamps of CTA 0 (tuning aid, CCQP_DEBUG_TIMING=1); null = off
     // row-sharded multi-GPU solves (world == 1: unused)
     XComm x;
@@ -108,6 +112,7 @@ struct DenseSmem {
     unsigned long long* ascratch;   // 32
 };
 
+constexpr int kNumMbar = 8;
 constexpr size_t kDenseSmemLimit = 220 * 1024;    // cudaFuncAttributeMaxDynamicSharedMemorySize of the dense kernels
 constexpr size_t kDenseSmemTarget = 200 * 1024;   // what the tiling aims to stay under
 
@@ -117,7 +122,7 @@ __host__ __device__ inline size_t dense_smem_bytes(int CW, int rows_max, int nse
     s += (size_t)rows_max * nseg * 8;
     s += kMaxRed * 32 * 8;
     s += 32 * 8;
-    s += 4 * 8;
+    s += kNumMbar * 8;
     return s + 128;
 }
 
@@ -127,7 +132,7 @@ struct Kst {                // per-thread kernel state
     int bid, nblk;          // this CTA's index in / the size of the rank's grid (blockIdx.x / gridDim.x unless ranks are emulated)
     int gtid, gstride;
     int r0, r1;             // rows of this CTA (global indices)
-    unsigned par[4];        // mbarrier phase parity per buffer (dense: 2 panel buffers; CSR: 4 ring stages)
+    unsigned parbits;       // mbarrier phase parities, bit i = barrier i (dense: 2 panel buffers; CSR: 4 column-id + 4 value stages)
     int yq;                 // next buffer of the mat-vec output pool
     long long mv, gemv, iters, draws;
 };
@@ -272,7 +277,8 @@ __device__ __forceinline__ double dot_seg_generic(const double* __restrict__ aro
 constexpr int kCsrTile = 4096;                       // independent of the launch shape (csr_tile_row is built for it)
 constexpr int kCsrE = kCsrTile / kDenseThreads;      // entries per thread per tile: 16 at 256 threads, 4 at 1024
 static_assert(kCsrE * kDenseThreads == kCsrTile && kCsrE >= 1, "threads per CTA must divide the CSR tile");
-constexpr int kCsrStages = 4;
+constexpr int kCsrStages = 4;                        // stages of the value ring and of the column-id ring
+constexpr int kCsrDesc = 8;                          // tile descriptors alive at a time (written 4 tiles ahead, read until the rows are summed)
 constexpr int kCsrStageBytes = kCsrTile * 12;         // values, then column ids
 constexpr int kCsrCW = kCsrStages * kCsrStageBytes / 16;   // "panel width" that makes the two panel buffers hold the ring
 constexpr int kCsrWin = kDenseThreads + 1;            // row pointers of a tile kept in shared memory
@@ -292,60 +298,66 @@ __device__ __forceinline__ void gemv_phase_csr(Kst& k, const DenseCtx& c, const 
     const int warp_gid0 = (tid & ~31) / G;                           // first group of this warp
     const int cr0 = k.r0 - c.row0, cr1 = k.r1 - c.row0;               // this CTA's rows, relative to the shard
     volatile double* carry_slot = k.sm.scratch;                       // [2], by tile parity
-    int4* dsc = reinterpret_cast<int4*>(k.sm.scratch + 4);            // [kCsrStages][2]: per-tile descriptors, written by thread 0
+    int4* dsc = reinterpret_cast<int4*>(k.sm.scratch + 4);            // [kCsrDesc][2]: per-tile descriptors, written by thread 0
     int* win = reinterpret_cast<int*>(k.sm.psum);                     // [2][kCsrWin], by tile parity: tile-relative row pointers
     unsigned char* ring = reinterpret_cast<unsigned char*>(k.sm.vbuf[0]);
+    double* const val_ring = reinterpret_cast<double*>(ring);                                     // [kCsrStages][kCsrTile] values -> products
+    int* const idx_ring = reinterpret_cast<int*>(ring + (size_t)kCsrStages * kCsrTile * 8);       // [kCsrStages][kCsrTile] column ids
+    uint64_t* const ibar = k.sm.mbar;                                 // column-id stages
+    uint64_t* const vbar = k.sm.mbar + kCsrStages;                    // value stages
     const long long P0 = cr1 > cr0 ? c.csr_ptr[cr0] : 0, P1 = cr1 > cr0 ? c.csr_ptr[cr1] : 0;
     if (P1 > P0) {                                                    // CTA-uniform
         const long long g0 = P0 / kCsrTile;
         const int nt = (int)((P1 - 1) / kCsrTile - g0) + 1;
-        // Thread 0 describes a tile ONCE for everybody when it starts the tile's copies: {first row (open since the previous
-        // tile, or the CTA's first), rows, this CTA's entry range [lo, hi) inside the tile}, {entries, slow path}.  All positions
-        // inside a tile are 32-bit and tile-relative from here on: the 64-bit row pointers are touched once per row.
-        auto issue = [&](int t) {                                     // thread 0 only
-            const long long nnz = c.csr_ptr[c.nrows];
+        // Thread 0 describes a tile ONCE for everybody when it starts the copy of the tile's column ids: {first row (open since
+        // the previous tile, or the CTA's first), rows, this CTA's entry range [lo, hi) inside the tile}, {entries, slow path}.
+        // All positions inside a tile are 32-bit and tile-relative from here on: the 64-bit row pointers are touched once per row.
+        auto tile_cnt = [&](int t) { const long long nnz = c.csr_ptr[c.nrows], T = (g0 + t) * kCsrTile; return (int)(nnz - T < kCsrTile ? nnz - T : kCsrTile); };
+        auto tile_slow = [&](int cnt) { return ((cnt & 3) || !c.csr_tma) ? 1 : 0; };   // ragged final tile of the stream / unaligned arrays
+        auto issue_idx = [&](int t) {                                 // thread 0 only
             const long long T = (g0 + t) * kCsrTile;
-            const int cnt = (int)(nnz - T < kCsrTile ? nnz - T : kCsrTile);
-            const int slow = ((cnt & 3) || !c.csr_tma) ? 1 : 0;       // ragged final tile of the stream / unaligned arrays: ordinary loads
+            const int cnt = tile_cnt(t), slow = tile_slow(cnt);
             int r_cur = t == 0 ? cr0 : c.csr_tile_row[g0 + t], r_last = c.csr_tile_row[g0 + t + 1];
             if (r_last > cr1 - 1 || T + cnt >= P1) r_last = cr1 - 1;
             const int lo = (int)((T > P0 ? T : P0) - T), hi = (int)((T + cnt < P1 ? T + cnt : P1) - T);
-            const int st = t % kCsrStages;
-            dsc[2 * st] = make_int4(r_cur, r_last - r_cur + 1, lo, hi);
-            dsc[2 * st + 1] = make_int4(cnt, slow, 0, 0);
+            dsc[2 * (t % kCsrDesc)] = make_int4(r_cur, r_last - r_cur + 1, lo, hi);
+            dsc[2 * (t % kCsrDesc) + 1] = make_int4(cnt, slow, 0, 0);
             if (slow) return;
-            unsigned char* dst = ring + (size_t)st * kCsrStageBytes;
-            mbar_expect_tx(&k.sm.mbar[st], (uint32_t)cnt * 12u);
-            bulk_g2s_evict_first(dst, c.csr_val + T, (uint32_t)cnt * 8u, &k.sm.mbar[st]);
-            bulk_g2s_evict_first(dst + kCsrTile * 8, c.csr_idx + T, (uint32_t)cnt * 4u, &k.sm.mbar[st]);
+            const int st = t % kCsrStages;
+            mbar_expect_tx(&ibar[st], (uint32_t)cnt * 4u);
+            bulk_g2s_evict_first(idx_ring + (size_t)st * kCsrTile, c.csr_idx + T, (uint32_t)cnt * 4u, &ibar[st]);
+        };
+        auto issue_val = [&](int t) {                                 // thread 0 only
+            const int cnt = tile_cnt(t);
+            if (tile_slow(cnt)) return;
+            const int st = t % kCsrStages;
+            mbar_expect_tx(&vbar[st], (uint32_t)cnt * 8u);
+            bulk_g2s_evict_first(val_ring + (size_t)st * kCsrTile, c.csr_val + (g0 + t) * kCsrTile, (uint32_t)cnt * 8u, &vbar[st]);
         };
         if (tid == 0) {
             carry_slot[0] = 0.0;
             fence_proxy_async();
-            for (int t = 0; t < nt && t < kCsrStages; ++t) issue(t);
+            for (int t = 0; t < nt && t < kCsrStages; ++t) { issue_idx(t); issue_val(t); }
         }
         __syncthreads();                                              // descriptors of the first tiles are visible
-        // Software pipeline over the tiles: the gather of tile t+1 is IN FLIGHT (kCsrE loads per thread, in registers)
-        // while the rows of tile t are summed; then the products of t+1 are formed and ONE barrier closes the step.
         struct Tile { int r_cur, nrows, lo, hi, cnt, slow; };
         auto describe = [&](int t) {
-            const int4 d0 = dsc[2 * (t % kCsrStages)], d1 = dsc[2 * (t % kCsrStages) + 1];
+            const int4 d0 = dsc[2 * (t % kCsrDesc)], d1 = dsc[2 * (t % kCsrDesc) + 1];
             Tile d; d.r_cur = d0.x; d.nrows = d0.y; d.lo = d0.z; d.hi = d0.w; d.cnt = d1.x; d.slow = d1.y;
             return d;
         };
         // pointer of row r as a position inside the tile that starts at T, clamped to [lo, hi + 1] (hi + 1 = "beyond this CTA's part")
         auto rel = [&](long long p, long long T, const Tile& d) { p -= T; return p < d.lo ? d.lo : (p > d.hi ? d.hi + 1 : (int)p); };
-        int j[kCsrE];
-        double x[kCsrE];
-        int wv = 0;
-        auto gather_issue = [&](int t, const Tile& d) {
+        // G(t): the gather of tile t leaves (kCsrE loads per thread, results in registers) + the tile's row pointers
+        auto gather_issue = [&](int t, double (&x)[kCsrE], long long& wv) {
+            const Tile d = describe(t);
             const int st = t % kCsrStages;
-            // row pointers of the tile's rows -> shared window (stored by finish_products): one coalesced load by as many threads as rows
-            if (tid <= d.nrows && tid < kCsrWin) wv = rel(c.csr_ptr[d.r_cur + tid], (g0 + t) * kCsrTile, d);
+            if (tid <= d.nrows && tid < kCsrWin) wv = c.csr_ptr[d.r_cur + tid];     // consumed a step later (finish_products)
             if (d.slow) return;
-            const int* idx = reinterpret_cast<const int*>(ring + (size_t)st * kCsrStageBytes + kCsrTile * 8);
-            mbar_wait(&k.sm.mbar[st], k.par[st]);
-            k.par[st] ^= 1u;
+            const int* idx = idx_ring + (size_t)st * kCsrTile;
+            mbar_wait(&ibar[st], (k.parbits >> st) & 1u);
+            k.parbits ^= 1u << st;
+            int j[kCsrE];
             if (d.cnt == kCsrTile) {
 #pragma unroll
                 for (int u = 0; u < kCsrE; ++u) j[u] = idx[u * kDenseThreads + tid];
@@ -356,17 +368,23 @@ __device__ __forceinline__ void gemv_phase_csr(Kst& k, const DenseCtx& c, const 
 #pragma unroll
             for (int u = 0; u < kCsrE; ++u) x[u] = c.csr_l1 ? ld_ca(v + j[u]) : ld_cg(v + j[u]);
         };
-        auto finish_products = [&](int t, const Tile& d) {
+        // F(t): products of tile t in place over its values (the gather left two steps ago), row-pointer window of the tile
+        auto finish_products = [&](int t, const double (&x)[kCsrE], long long wv) {
+            const Tile d = describe(t);
             const int st = t % kCsrStages;
-            double* prod = reinterpret_cast<double*>(ring + (size_t)st * kCsrStageBytes);
-            if (tid <= d.nrows && tid < kCsrWin) win[(t & 1) * kCsrWin + tid] = wv;
+            double* prod = val_ring + (size_t)st * kCsrTile;
+            if (tid <= d.nrows && tid < kCsrWin) win[(t & 1) * kCsrWin + tid] = rel(wv, (g0 + t) * kCsrTile, d);
             if (d.slow) {
                 const long long T = (g0 + t) * kCsrTile;
                 for (int q = tid; q < d.cnt; q += kDenseThreads) {
                     const double xv = c.csr_l1 ? ld_ca(v + __ldg(c.csr_idx + T + q)) : ld_cg(v + __ldg(c.csr_idx + T + q));
                     prod[q] = ldg_stream(c.csr_val + T + q) * xv;
                 }
-            } else if (d.cnt == kCsrTile) {
+                return;
+            }
+            mbar_wait(&vbar[st], (k.parbits >> (kCsrStages + st)) & 1u);
+            k.parbits ^= 1u << (kCsrStages + st);
+            if (d.cnt == kCsrTile) {
 #pragma unroll
                 for (int u = 0; u < kCsrE; ++u) prod[u * kDenseThreads + tid] *= x[u];
             } else {
@@ -374,18 +392,11 @@ __device__ __forceinline__ void gemv_phase_csr(Kst& k, const DenseCtx& c, const 
                 for (int u = 0; u < kCsrE; ++u) { const int q = u * kDenseThreads + tid; if (q < d.cnt) prod[q] *= x[u]; }
             }
         };
-        Tile cur = describe(0);
-        gather_issue(0, cur);
-        finish_products(0, cur);
-        __syncthreads();
-        for (int t = 0; t < nt; ++t) {
-            const int st = t % kCsrStages;
+        // R(t): the rows of tile t, summed from the products in shared memory
+        auto row_sums = [&](int t) {
+            const Tile cur = describe(t);
             const int* pw = win + (t & 1) * kCsrWin;
-            const double* prod = reinterpret_cast<const double*>(ring + (size_t)st * kCsrStageBytes);
-            // everybody is behind the barrier that ended step t-1: the stage (and the descriptor) of tile t-1 are free
-            if (tid == 0 && t >= 1 && t - 1 + kCsrStages < nt) { fence_proxy_async(); issue(t - 1 + kCsrStages); }
-            Tile nxt = cur;
-            if (t + 1 < nt) { nxt = describe(t + 1); gather_issue(t + 1, nxt); }
+            const double* prod = val_ring + (size_t)(t % kCsrStages) * kCsrTile;
             const double carry_in = carry_slot[t & 1];
             for (int kk = 0; kk * ngroups < cur.nrows; ++kk) {        // CTA-uniform trip count
                 if (warp_gid0 + kk * ngroups >= cur.nrows) continue;  // warp-uniform: nothing for this warp in this pass
@@ -406,15 +417,42 @@ __device__ __forceinline__ void gemv_phase_csr(Kst& k, const DenseCtx& c, const 
                 for (int o = G >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
                 if (glane == 0 && active) {
                     if (i == 0) acc = carry_in + acc;                 // earlier tiles' part of the row first
-                    if (complete) epi(c.row0 + r, acc);
+                    if (complete) c.ytmp[r] = acc;                    // the epilogue runs after the tile loop, all rows side by side
                     else carry_slot[(t + 1) & 1] = acc;               // the one row that continues into the next tile (the last one)
                 }
             }
-            if (t + 1 < nt) finish_products(t + 1, nxt);
-            cur = nxt;
+        };
+        // Software pipeline, two tiles deep: in step t the gather of tile t+2 LEAVES, the rows of tile t are summed, the
+        // products of tile t+1 (whose gather left a whole step ago) are formed, and ONE barrier closes the step: no step waits
+        // for memory.  The column ids of a tile are consumed two steps before its values, so they travel in separate rings
+        // (4 stages each): ids of tile t+4 and values of tile t+3 are requested at the top of step t.
+        double xa[kCsrE], xb[kCsrE];
+        long long wa = 0, wb = 0;
+        gather_issue(0, xa, wa);
+        if (nt > 1) gather_issue(1, xb, wb);
+        finish_products(0, xa, wa);
+        __syncthreads();
+        auto step = [&](int t, double (&x_even)[kCsrE], long long& w_even, double (&x_odd)[kCsrE], long long& w_odd) {
+            // tiles t and t+2 share (x_even, w_even); tile t+1 uses (x_odd, w_odd)
+            if (tid == 0) {               // everybody is behind the barrier that ended step t-1 (t = 0: the prologue's)
+                const bool i4 = t + kCsrStages < nt, v3 = t >= 1 && t - 1 + kCsrStages < nt;
+                if (i4 || v3) fence_proxy_async();
+                if (i4) issue_idx(t + kCsrStages);                    // id stage of tile t: read in step t-2
+                if (v3) issue_val(t - 1 + kCsrStages);                // value stage of tile t-1: summed in step t-1
+            }
+            if (t + 2 < nt) gather_issue(t + 2, x_even, w_even);
+            row_sums(t);
+            if (t + 1 < nt) finish_products(t + 1, x_odd, w_odd);
             __syncthreads();          // products + row-pointer window of tile t+1 and the carry of tile t are visible;
                                       // everybody has finished tile t
+        };
+        for (int t = 0; t < nt; t += 2) {
+            step(t, xa, wa, xb, wb);
+            if (t + 1 < nt) step(t + 1, xb, wb, xa, wa);
         }
+        // epilogue pass: one row per thread at a time, so the loads an epilogue does (e.g. SPG's d_r for d.Ad) overlap across
+        // rows instead of stalling the tile loop once per tile (the last step's barrier made the row sums visible to the CTA)
+        for (int r = cr0 + tid; r < cr1; r += kDenseThreads) epi(c.row0 + r, ld_cg(c.ytmp + r));
     } else {
         for (int r = cr0 + tid; r < cr1; r += kDenseThreads) epi(c.row0 + r, 0.0);     // a range of empty rows
     }
@@ -426,7 +464,7 @@ __device__ __forceinline__ void gemv_phase_csr(Kst& k, const DenseCtx& c, const 
 // v: full-length global vector (npad entries, zero tail), complete before the phase starts.
 template <class Epi>
 __device__ __forceinline__ void gemv_phase(Kst& k, const DenseCtx& c, const double* v, Epi epi) {
-    if (CCQP_CSR_ONLY || c.csr_val) { gemv_phase_csr(k, c, v, epi); return; }
+    if constexpr (!CCQP_DENSE_ONLY) { if (CCQP_CSR_ONLY || c.csr_val) { gemv_phase_csr(k, c, v, epi); return; } }
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = c.n, CW = c.CW, SW = c.SW, np = c.np, nseg = c.nseg;
     const int nrows_cta = k.r1 - k.r0;
@@ -445,8 +483,8 @@ __device__ __forceinline__ void gemv_phase(Kst& k, const DenseCtx& c, const doub
     }
     for (int p = 0; p < np; ++p) {
         const int buf = p & 1;
-        mbar_wait(&k.sm.mbar[buf], k.par[buf]);
-        k.par[buf] ^= 1u;
+        mbar_wait(&k.sm.mbar[buf], (k.parbits >> buf) & 1u);
+        k.parbits ^= 1u << buf;
         const int pc = panel_cols(p);
         const int spp = (pc + SW - 1) / SW;
         const int ntask = nrows_cta * spp;
@@ -1087,7 +1125,7 @@ __device__ __forceinline__ void dense_body(const DenseCtx& c, const int bid, con
     k.gstride = nblk * kDenseThreads;
     k.r0 = c.row0 + (int)(((long long)c.nrows * bid) / nblk);
     k.r1 = c.row0 + (int)(((long long)c.nrows * (bid + 1)) / nblk);
-    if (c.csr_val) {    // CSR: nnz-balanced, row-aligned split (first row whose start is at or beyond bid * nnz / G)
+    if (!CCQP_DENSE_ONLY && c.csr_val) {    // CSR: nnz-balanced, row-aligned split (first row whose start is at or beyond bid * nnz / G)
         const long long nnz = c.csr_ptr[c.nrows];
         auto first_row_at = [&](long long target) {
             int lo = 0, hi = c.nrows;                                 // smallest r in [0, nrows] with csr_ptr[r] >= target
@@ -1097,11 +1135,11 @@ __device__ __forceinline__ void dense_body(const DenseCtx& c, const int bid, con
         k.r0 = c.row0 + (bid == 0 ? 0 : first_row_at(nnz / nblk * bid + nnz % nblk * bid / nblk));
         k.r1 = c.row0 + (bid == nblk - 1 ? c.nrows : first_row_at(nnz / nblk * (bid + 1) + nnz % nblk * (bid + 1) / nblk));
     }
-    k.par[0] = k.par[1] = k.par[2] = k.par[3] = 0u;
+    k.parbits = 0u;
     k.mv = k.gemv = k.iters = k.draws = 0;
     k.yq = 0;
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 4; ++i) mbar_init(&k.sm.mbar[i], 1);
+        for (int i = 0; i < kNumMbar; ++i) mbar_init(&k.sm.mbar[i], 1);
         mbar_fence_init();
     }
     __syncthreads();

@@ -1,0 +1,17 @@
+#!/bin/bash
+# round 2, pass l: dense kernels without CSR code, CSR epilogue pass + deferred pointer conversion, whole suite
+out=gpurun_out; tag=r02l
+mkdir -p $out
+timeout 300 python tools/ab_apgd.py 2>&1 | tail -1
+echo "n=4096"; timeout 300 python tools/bench_n4096.py 2>&1 | tail -1
+timeout 1700 python -m pytest tests -m gpu -q > $out/${tag}_pytest.log 2>&1; echo "pytest rc=$?"; tail -4 $out/${tag}_pytest.log
+for g in 4 8; do echo "CSR_GROUP=$g"; CCQP_CSR_GROUP=$g timeout 300 python tools/profile_csr.py 2>&1 | grep "csr gemv\|max rel"; done
+CCQP_DEBUG_TIMING=1 timeout 300 python tools/profile_csr.py --solve 2>&1 | grep -v Warn | tail -3
+timeout 600 python tools/bench_sparse.py > $out/${tag}_sparse.json 2> $out/${tag}_sparse.err; echo "sparse rc=$?"; python - <<'PY'
+import json
+d = json.load(open("gpurun_out/r02l_sparse.json"))
+for k, v in d.items(): print(k, {a: (round(b["GBps"]), round(b["us_per_matvec"], 1), b["mv"]) for a, b in v.items() if isinstance(b, dict)})
+PY
+REPS=1 python tools/profile_csr.py > $out/${tag}_csr_plain.log 2>&1 &&
+REPS=1 ncu --set full --clock-control none --import-source on -k regex:'dense_kernel' -s 1 -c 1 -f -o $out/${tag}_csr python tools/profile_csr.py > $out/${tag}_csr_ncu.log 2>&1
+echo "ncu rc=$?"
