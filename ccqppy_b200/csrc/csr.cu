@@ -3,12 +3,14 @@
 // The CSR mat-vec phase is a gather: latency-bound, it wants many resident warps and few registers, the opposite of
 // the dense phase (8 warps x 254 registers so that 16 256-bit loads per lane are in flight).  So the SAME solver
 // programs (dense.cuh) are compiled a second time here with a different launch shape -- CCQP_CSR_THREADS threads per
-// CTA (1 CTA per SM, 65536 / threads registers per thread), the dense mat-vec loop compiled out (CCQP_CSR_ONLY) --
+// CTA (1 CTA per SM, 65536 / threads registers per thread; measured on n = 2^20, 57 entries per row, SPG, us per mat-vec:
+// 256 threads 333, 512 threads 292, 1024 threads 399 -- at 64 registers the solver programs spill into the tile loop),
+// the dense mat-vec loop compiled out (CCQP_CSR_ONLY) --
 // inside their own namespace: every `ccqp::` entity of the headers becomes `ccqp_csr::` in this file, so the two
 // compilations of the templates cannot collide.  capi.cu routes every launch of a handle that holds a CSR matrix
 // through csr_variant_launch(); the context struct is the same plain-data struct in both namespaces.
 #ifndef CCQP_CSR_THREADS
-#define CCQP_CSR_THREADS 1024
+#define CCQP_CSR_THREADS 512
 #endif
 #define CCQP_DENSE_THREADS CCQP_CSR_THREADS
 #define CCQP_CSR_ONLY 1
