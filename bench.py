@@ -132,7 +132,7 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.t0 = index, [], None, None
 
     def start(self):
         try:
@@ -146,7 +146,12 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def mark(self):
+        """The timed region starts now (the sampler itself is started before the warm-up: nvidia-smi needs a few hundred
+        milliseconds to come up, more than a short timed region at 8 GPUs lasts)."""
+        self.t0 = time.time()
 
     def stop(self):
         if not self.proc:
@@ -159,7 +164,12 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        t0 = self.t0 if self.t0 is not None else 0.0
+        rows = [r for t, r in self.rows if t >= t0]
+        window = "timed region"
+        if not rows:        # the timed region was shorter than one sampling period: the warm-up ran the same kernels
+            rows, window = [r for _, r in self.rows], "warm-up + timed region (the timed region is shorter than one sampling period)"
+        for r in rows:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
                 for nm, v in zip(names, r[3:7]):
@@ -168,7 +178,7 @@ class ClockSampler:
             except Exception:
                 pass
         return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
-                    reasons=sorted(reasons), samples=len(sm))
+                    reasons=sorted(reasons), samples=len(sm), window=window)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -470,11 +480,12 @@ def main():
             spg.solve(A, b, convex_proj_op=op, uniforms=uni_dev)
             return spg
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         r = device_step()
     sync_all()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.mark()
     r, dt, kern_s, mvs, launches = timed_solves(device_step, args.steps, sync_all)
     clocks = sampler.stop()
     if world > 1:

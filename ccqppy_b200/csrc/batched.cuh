@@ -1,33 +1,36 @@
-// Batched mode: thousands of small independent box-constrained QPs (n <= 64), one CTA (64 threads)
-// per problem at a time, the whole solver loop of the reference inside one persistent kernel (no
-// host round trips).  Problem i is CCQPSolverX(tol,max_mv).solve(A[i], b[i], x0[i], BoxProjOp(n, lb[i], ub[i]))
-// (solvers.py:94/220/393/583/719/878 with solution_spaces.py:280-366).
+// Batched mode: thousands of small independent QPs (n <= 128), one CTA per problem at a time, the whole solver loop of the
+// reference inside one persistent kernel (no host round trips).  Problem i is
+//     CCQPSolverX(tol,max_mv).solve(A[i], b[i], x0[i], BoxProjOp(n, lb[i], ub[i]))          (ccqp_solve_batched)
+// or  CCQPSolverX(tol,max_mv).solve(A[i], b[i], x0[i], op)  with ONE operator of any kind    (ccqp_solve_batched_table)
+// (solvers.py:94/220/393/583/719/878/1026 with solution_spaces.py:77-560).
 //
 // Data path per problem (n = 64: 32 KB of A, 2 KB of vectors in, 512 B out):
-//   * A lives in REGISTERS for the whole solve.  Thread t = 4*rb + cb keeps the 4 x 16 sub-block
-//     A[4rb .. 4rb+3][16cb .. 16cb+15] (64 doubles), loaded straight from HBM/L2 with 16 256-bit
-//     read-only loads (each lane fetches one full 32-byte sector).  The problem AFTER the current one
-//     is pulled into L2 with one bulk-prefetch instruction (TMA engine, UBLKPF) while the current
-//     one iterates, so the register fill of the next problem is an L2 hit.
-//   * mat-vec: the input vector is published through a double-buffered 512-byte shared array (one
-//     barrier); a thread reads only its 16-entry slice (8 LDS.128), does 64 DFMAs (4 rows x 16
-//     columns, 8 independent chains) and the four lanes of a row block combine their 4 partial rows
-//     with a 2-stage exchange butterfly (3 SHFL.64 + 3 DADD) after which thread t holds y_t.
-//     Why not "thread t keeps row t" (the first version of this kernel): every thread then reads all
-//     64 entries of x per mat-vec, and a warp-wide LDS.128 occupies the shared-memory crossbar for
-//     4 cycles (512 bytes delivered) whether or not the lanes read the same address: 256 crossbar
-//     cycles per mat-vec per problem against 64 cycles of FP64 pipe.  ncu showed exactly that
-//     (shared-memory wavefronts 59 %, FP64 pipe 32 %; profiles/r01_ncu_full_first.csv).  The 4x16
-//     blocking cuts the crossbar work per mat-vec from 256 to ~80 cycles.
-//   * dot products: K <= 4 sums are reduced together with an exchange butterfly (6 SHFL.64 + 6 DADD
-//     for K = 3 instead of 15 + 15), then the two warps swap through shared memory (one barrier).
-//   * stopping tests compare the SQUARED residual with a host-computed threshold that is exactly
-//     equivalent to the reference's sqrt(.) < tol (sqrt is monotone), so no sqrt is on the
-//     per-iteration critical path; the reported residual is computed once at the end.
-//   * everything else (projection, axpy, step lengths) is per-thread register arithmetic, with the
-//     reference's rounding (compiled with -fmad=false; explicit fma() only in the sums).
-//   Problems are handed out through an atomic counter (iteration counts differ per problem);
-//   results do not depend on the schedule.
+//   * A lives in REGISTERS for the whole solve.  n <= 64: 64 threads, thread t = 8*rb + cb keeps the 8 x 8 sub-block
+//     A[8rb .. 8rb+7][8cb .. 8cb+7] (64 doubles = 128 registers), 6 CTAs per SM.  64 < n <= 128: 256 threads, a 16 x 16 grid
+//     of the same 8 x 8 sub-blocks, one CTA per SM (struct BL<NT>).  The problem AFTER the current one travels into a padded
+//     shared-memory tile by TMA row copies (cp.async.bulk + one mbarrier; its b / lb / ub rows ride on the same mbarrier)
+//     while the current one iterates; the register fill from the tile is conflict-free LDS.128.  The work queue is two
+//     problems deep, so neither the atomic that hands out problems nor any global load sits on a problem's dependent chain.
+//   * mat-vec: the input vector is published through a double-buffered, bank-padded shared array (one barrier); a thread reads
+//     only its 8-entry slice (4 LDS.128), does 64 DFMAs (8 rows x 8 columns, 8 independent chains) and the lanes of a row
+//     block combine their partial rows with a 3-stage exchange butterfly (7 SHFL.64 + 7 DADD) after which the thread holds y
+//     of the unknown it owns.
+//     Why not "thread t keeps row t" (the first version of this kernel): every thread then reads all 64 entries of x per
+//     mat-vec, and a warp-wide LDS.128 occupies the shared-memory crossbar for 4 cycles (512 bytes delivered) whether or
+//     not the lanes read the same address: 256 crossbar cycles per mat-vec per problem against 64 cycles of FP64 pipe.  ncu
+//     showed exactly that (shared-memory wavefronts 59 %, FP64 pipe 32 %; profiles/r01_ncu_full_first.csv).  The 8 x 8
+//     blocking needs 32 crossbar cycles for x plus 28 for the shuffles.  (A 4 x 16 blocking, 2-stage butterfly but 8 LDS.128
+//     per thread, measured slower and was removed in round 2.)
+//   * dot products: K <= 4 sums are reduced together with an exchange butterfly (6 SHFL.64 + 6 DADD for K = 3 instead of
+//     15 + 15), then the warps swap through shared memory (one barrier).  CCQP_BATCHED_DMMA=1 runs the 32-lane sums on the
+//     FP64 tensor path instead (measured equal).
+//   * stopping tests compare the SQUARED residual with a host-computed threshold that is exactly equivalent to the
+//     reference's sqrt(.) < tol (sqrt is monotone), so no sqrt is on the per-iteration critical path; the reported
+//     residual is computed once at the end.
+//   * everything else (projection, axpy, step lengths) is per-thread register arithmetic, with the reference's rounding
+//     (compiled with -fmad=false; explicit fma() only in the sums).
+//   Problems are handed out through an atomic counter (iteration counts differ per problem); results do not depend on the
+//   schedule.
 //
 // Bounds: HBM bytes/problem = 8 n^2 + 32 n (+8 n for x0, + uniforms read by SPG);
 //         fp64 flops/problem = 2 n^2 * (mat-vecs executed).

@@ -409,10 +409,16 @@ __device__ __forceinline__ void gemv_phase_csr(Kst& k, const DenseCtx& c, const 
                 }
                 const bool complete = active && p1 <= cur.hi;         // the row ends inside this CTA's part of the tile
                 const int hi = p1 < cur.hi ? p1 : cur.hi;
+                // lane glane takes entries start + glane, + G, + 2G, ...: even ones into a0, odd ones into a1, eight loads in
+                // flight at a time (the warps that sum rows are the critical path of the step: everybody else waits for them)
                 double a0 = 0.0, a1 = 0.0;
-                int q = (p0 < cur.hi ? p0 : cur.hi) + glane;
-                for (; q + G < hi; q += 2 * G) { a0 += prod[q]; a1 += prod[q + G]; }
-                if (q < hi) a0 += prod[q];
+                for (int q = (p0 < cur.hi ? p0 : cur.hi) + glane; q < hi; q += 8 * G) {
+                    double pv[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) pv[u] = (q + u * G < hi) ? prod[q + u * G] : 0.0;
+#pragma unroll
+                    for (int u = 0; u < 8; u += 2) { a0 += pv[u]; a1 += pv[u + 1]; }
+                }
                 double acc = a0 + a1;
                 for (int o = G >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
                 if (glane == 0 && active) {

@@ -27,3 +27,5 @@ echo "ncu batched rc=$?"
 REPS=1 python tools/profile_csr.py > $out/${tag}_plain_csr.log 2>&1 &&
 REPS=1 ncu --set full --clock-control none --import-source on -k regex:'dense_kernel' -s 1 -c 1 -f -o $out/${tag}_csr python tools/profile_csr.py > $out/${tag}_ncu_csr.log 2>&1
 echo "ncu csr rc=$?"; cat $out/${tag}_plain_csr.log | grep "csr gemv"
+for mb in 0 64; do echo "shard mat-vec, L2_RESIDENT_MB=$mb"; CCQP_L2_RESIDENT_MB=$mb timeout 300 python tools/shard_gemv_time.py 2>&1 | grep "P="; done
+CCQP_DEBUG_TIMING=1 timeout 300 python tools/profile_csr.py --solve 2>&1 | grep -v Warn | tail -2
