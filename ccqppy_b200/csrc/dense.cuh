@@ -312,12 +312,20 @@ __device__ __forceinline__ void gemv_phase_csr(Kst& k, const DenseCtx& c, const 
         // Thread 0 describes a tile ONCE for everybody when it starts the copy of the tile's column ids: {first row (open since
         // the previous tile, or the CTA's first), rows, this CTA's entry range [lo, hi) inside the tile}, {entries, slow path}.
         // All positions inside a tile are 32-bit and tile-relative from here on: the 64-bit row pointers are touched once per row.
-        auto tile_cnt = [&](int t) { const long long nnz = c.csr_ptr[c.nrows], T = (g0 + t) * kCsrTile; return (int)(nnz - T < kCsrTile ? nnz - T : kCsrTile); };
+        const long long nnz = c.csr_ptr[c.nrows];
+        auto tile_cnt = [&](int t) { const long long T = (g0 + t) * kCsrTile; return (int)(nnz - T < kCsrTile ? nnz - T : kCsrTile); };
         auto tile_slow = [&](int cnt) { return ((cnt & 3) || !c.csr_tma) ? 1 : 0; };   // ragged final tile of the stream / unaligned arrays
-        auto issue_idx = [&](int t) {                                 // thread 0 only
+        // thread 0 issues the tiles in order; the two csr_tile_row entries a descriptor needs are fetched one issue ahead
+        // (tr_a = csr_tile_row[g0 + t], tr_b = csr_tile_row[g0 + t + 1] for the NEXT tile t to be issued), so that the thread
+        // everybody waits for at the step's barrier never sits on an L2 round trip of its own
+        int tr_a = 0, tr_b = 0;
+        if (tid == 0) { tr_a = c.csr_tile_row[g0]; tr_b = c.csr_tile_row[g0 + 1]; }
+        auto issue_idx = [&](int t) {                                 // thread 0 only, t = 0, 1, 2, ... in order
             const long long T = (g0 + t) * kCsrTile;
             const int cnt = tile_cnt(t), slow = tile_slow(cnt);
-            int r_cur = t == 0 ? cr0 : c.csr_tile_row[g0 + t], r_last = c.csr_tile_row[g0 + t + 1];
+            int r_cur = t == 0 ? cr0 : tr_a, r_last = tr_b;
+            tr_a = tr_b;
+            if (t + 1 < nt) tr_b = c.csr_tile_row[g0 + t + 2];        // consumed by the next issue, a step from now
             if (r_last > cr1 - 1 || T + cnt >= P1) r_last = cr1 - 1;
             const int lo = (int)((T > P0 ? T : P0) - T), hi = (int)((T + cnt < P1 ? T + cnt : P1) - T);
             dsc[2 * (t % kCsrDesc)] = make_int4(r_cur, r_last - r_cur + 1, lo, hi);

@@ -183,6 +183,23 @@ def test_determinism_run_to_run():
         assert o["mv"] == outs[0]["mv"] and np.array_equal(o["solution"], outs[0]["solution"])
 
 
+@pytest.mark.parametrize("solver", [pr.APGD, pr.BBPGD, pr.SPG, pr.MPRGP])
+def test_sync_protocols_and_l2_slice_do_not_change_a_bit(solver, monkeypatch):
+    """The closer-less rank-local grid sync adds the CTAs' partials in the closer's order, and the L2-resident slice of A
+    only changes a cache policy: a solve is bit-identical with either sync protocol and with or without the slice."""
+    n = 3600                                   # A = 104 MB: larger than the 96 MB above which A is streamed evict-first
+    A, b = pr.shift_problem(n, 9, 0.05)
+    tab = pr.mixed_table(n)
+    base = run_gpu(solver, A, b, tab, tol=1e-7, max_mv=1500, spg_seed=3)
+    for env in ({"CCQP_SYNC_CLOSERLESS": "0"}, {"CCQP_L2_RESIDENT_MB": "0"}, {"CCQP_SYNC_CLOSERLESS": "0", "CCQP_L2_RESIDENT_MB": "96"}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        o = run_gpu(solver, A, b, tab, tol=1e-7, max_mv=1500, spg_seed=3)
+        for k in env:
+            monkeypatch.delenv(k)
+        assert o["mv"] == base["mv"] and o["residual"] == base["residual"] and np.array_equal(o["solution"], base["solution"]), env
+
+
 @pytest.mark.parametrize("solver", [pr.PGD, pr.APGD, pr.BBPGD, pr.SPG, pr.MPRGP])
 def test_dense_4096_config2_against_oracle(solver):
     """Config 2: random dense SPD n=4096, box constraints, all five solvers, vs the oracle on the
