@@ -412,7 +412,8 @@ __device__ __forceinline__ void gemv_phase_csr(Kst& k, const DenseCtx& c, const 
                 const bool active = i < cur.nrows;
                 int p0 = cur.hi, p1 = cur.hi;
                 if (active) {
-                    if (i + 1 < kCsrWin) { p0 = pw[i]; p1 = pw[i + 1]; }
+                    if (i + 1 < kDenseThreads) { p0 = pw[i]; p1 = pw[i + 1]; }      // the window holds the pointers of rows 0 .. threads-1
+                                                                                       // (slot i is filled by thread i); beyond it: global loads
                     else { const long long T = (g0 + t) * kCsrTile; p0 = rel(c.csr_ptr[r], T, cur); p1 = rel(c.csr_ptr[r + 1], T, cur); }
                 }
                 const bool complete = active && p1 <= cur.hi;         // the row ends inside this CTA's part of the tile
