@@ -34,6 +34,9 @@ namespace ccqp {
 #ifndef CCQP_UNROLL
 #define CCQP_UNROLL 16
 #endif
+#ifndef CCQP_DENSE_LDS
+#define CCQP_DENSE_LDS 0      // 1: the dense loop reads the staged vector panel with explicit ld.shared (A/B build, profiles/README.md)
+#endif
 #ifndef CCQP_CSR_ONLY
 #define CCQP_CSR_ONLY 0       // 1: the dense mat-vec loop is compiled out (csr.cu: the many-warps build of the solver programs)
 #endif
@@ -198,9 +201,18 @@ __device__ __forceinline__ void dot_chunks(const double* ap, const double* vp, d
     double r[U][4];
 #pragma unroll
     for (int u = 0; u < U; ++u) ldg256_stream<kEF>(ap + (size_t)u * 128, r[u]);
+#if CCQP_DENSE_LDS
+    const uint32_t vp32 = smem_u32(vp);       // explicit LDS.128 pairs instead of the generic LD.E.128 the compiler emits for vp
+#endif
 #pragma unroll
     for (int u = 0; u < U; ++u) {
+#if CCQP_DENSE_LDS
+        double4 v;
+        asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(vp32 + (uint32_t)u * 1024u));
+        asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.z), "=d"(v.w) : "r"(vp32 + (uint32_t)u * 1024u + 16u));
+#else
         const double4 v = *reinterpret_cast<const double4*>(vp + (size_t)u * 128);
+#endif
         a0 = fma(r[u][0], v.x, a0);
         a1 = fma(r[u][1], v.y, a1);
         a2 = fma(r[u][2], v.z, a2);
@@ -294,38 +306,51 @@ __device__ __forceinline__ void bulk_g2s_evict_first(void* dst_smem, const void*
 template <class Epi>
 __device__ __forceinline__ void gemv_phase_csr(Kst& k, const DenseCtx& c, const double* v, Epi epi) {
     const int tid = threadIdx.x;
+    // register copies of what the phase reads from the context: in the outlined form (gemv_phase_csr_outlined) `c` is a
+    // reference into parameter memory, and every shared-memory access below is a compiler barrier for such loads
+    const long long* const csr_ptr = c.csr_ptr;
+    const int* const csr_idx = c.csr_idx;
+    const double* const csr_val = c.csr_val;
+    const int* const csr_tile_row = c.csr_tile_row;
+    double* const ytmp = c.ytmp;
+    const int row0 = c.row0, csr_l1 = c.csr_l1, csr_tma = c.csr_tma, shard_rows = c.nrows;
     const int G = c.csr_group, glane = tid & (G - 1), gid = tid / G, ngroups = kDenseThreads / G;
     const int warp_gid0 = (tid & ~31) / G;                           // first group of this warp
-    const int cr0 = k.r0 - c.row0, cr1 = k.r1 - c.row0;               // this CTA's rows, relative to the shard
-    volatile double* carry_slot = k.sm.scratch;                       // [2], by tile parity
-    int4* dsc = reinterpret_cast<int4*>(k.sm.scratch + 4);            // [kCsrDesc][2]: per-tile descriptors, written by thread 0
-    int* win = reinterpret_cast<int*>(k.sm.psum);                     // [2][kCsrWin], by tile parity: tile-relative row pointers
+    const int cr0 = k.r0 - row0, cr1 = k.r1 - row0;               // this CTA's rows, relative to the shard
+    // every shared-memory array of the phase is addressed explicitly (SharedArr: ld.shared / st.shared whatever the compiler
+    // still knows about the pointers kept in Kst)
+    const SharedArr<double> carry_slot(k.sm.scratch);                 // [2], by tile parity
+    const SharedArr<int4> dsc(k.sm.scratch + 4);                      // [kCsrDesc][2]: per-tile descriptors, written by thread 0
+    const SharedArr<int> win(k.sm.psum);                              // [2][kCsrWin], by tile parity: tile-relative row pointers
     unsigned char* ring = reinterpret_cast<unsigned char*>(k.sm.vbuf[0]);
     double* const val_ring = reinterpret_cast<double*>(ring);                                     // [kCsrStages][kCsrTile] values -> products
     int* const idx_ring = reinterpret_cast<int*>(ring + (size_t)kCsrStages * kCsrTile * 8);       // [kCsrStages][kCsrTile] column ids
+    const SharedArr<double> val_sh(val_ring);
+    const SharedArr<int> idx_sh(idx_ring);
     uint64_t* const ibar = k.sm.mbar;                                 // column-id stages
     uint64_t* const vbar = k.sm.mbar + kCsrStages;                    // value stages
-    const long long P0 = cr1 > cr0 ? c.csr_ptr[cr0] : 0, P1 = cr1 > cr0 ? c.csr_ptr[cr1] : 0;
+    unsigned parbits = k.parbits;                                     // a register copy for the phase (Kst may live in local memory)
+    const long long P0 = cr1 > cr0 ? csr_ptr[cr0] : 0, P1 = cr1 > cr0 ? csr_ptr[cr1] : 0;
     if (P1 > P0) {                                                    // CTA-uniform
         const long long g0 = P0 / kCsrTile;
         const int nt = (int)((P1 - 1) / kCsrTile - g0) + 1;
         // Thread 0 describes a tile ONCE for everybody when it starts the copy of the tile's column ids: {first row (open since
         // the previous tile, or the CTA's first), rows, this CTA's entry range [lo, hi) inside the tile}, {entries, slow path}.
         // All positions inside a tile are 32-bit and tile-relative from here on: the 64-bit row pointers are touched once per row.
-        const long long nnz = c.csr_ptr[c.nrows];
+        const long long nnz = csr_ptr[shard_rows];
         auto tile_cnt = [&](int t) { const long long T = (g0 + t) * kCsrTile; return (int)(nnz - T < kCsrTile ? nnz - T : kCsrTile); };
-        auto tile_slow = [&](int cnt) { return ((cnt & 3) || !c.csr_tma) ? 1 : 0; };   // ragged final tile of the stream / unaligned arrays
+        auto tile_slow = [&](int cnt) { return ((cnt & 3) || !csr_tma) ? 1 : 0; };   // ragged final tile of the stream / unaligned arrays
         // thread 0 issues the tiles in order; the two csr_tile_row entries a descriptor needs are fetched one issue ahead
         // (tr_a = csr_tile_row[g0 + t], tr_b = csr_tile_row[g0 + t + 1] for the NEXT tile t to be issued), so that the thread
         // everybody waits for at the step's barrier never sits on an L2 round trip of its own
         int tr_a = 0, tr_b = 0;
-        if (tid == 0) { tr_a = c.csr_tile_row[g0]; tr_b = c.csr_tile_row[g0 + 1]; }
+        if (tid == 0) { tr_a = csr_tile_row[g0]; tr_b = csr_tile_row[g0 + 1]; }
         auto issue_idx = [&](int t) {                                 // thread 0 only, t = 0, 1, 2, ... in order
             const long long T = (g0 + t) * kCsrTile;
             const int cnt = tile_cnt(t), slow = tile_slow(cnt);
             int r_cur = t == 0 ? cr0 : tr_a, r_last = tr_b;
             tr_a = tr_b;
-            if (t + 1 < nt) tr_b = c.csr_tile_row[g0 + t + 2];        // consumed by the next issue, a step from now
+            if (t + 1 < nt) tr_b = csr_tile_row[g0 + t + 2];        // consumed by the next issue, a step from now
             if (r_last > cr1 - 1 || T + cnt >= P1) r_last = cr1 - 1;
             const int lo = (int)((T > P0 ? T : P0) - T), hi = (int)((T + cnt < P1 ? T + cnt : P1) - T);
             dsc[2 * (t % kCsrDesc)] = make_int4(r_cur, r_last - r_cur + 1, lo, hi);
@@ -333,14 +358,14 @@ __device__ __forceinline__ void gemv_phase_csr(Kst& k, const DenseCtx& c, const 
             if (slow) return;
             const int st = t % kCsrStages;
             mbar_expect_tx(&ibar[st], (uint32_t)cnt * 4u);
-            bulk_g2s_evict_first(idx_ring + (size_t)st * kCsrTile, c.csr_idx + T, (uint32_t)cnt * 4u, &ibar[st]);
+            bulk_g2s_evict_first(idx_ring + (size_t)st * kCsrTile, csr_idx + T, (uint32_t)cnt * 4u, &ibar[st]);
         };
         auto issue_val = [&](int t) {                                 // thread 0 only
             const int cnt = tile_cnt(t);
             if (tile_slow(cnt)) return;
             const int st = t % kCsrStages;
             mbar_expect_tx(&vbar[st], (uint32_t)cnt * 8u);
-            bulk_g2s_evict_first(val_ring + (size_t)st * kCsrTile, c.csr_val + (g0 + t) * kCsrTile, (uint32_t)cnt * 8u, &vbar[st]);
+            bulk_g2s_evict_first(val_ring + (size_t)st * kCsrTile, csr_val + (g0 + t) * kCsrTile, (uint32_t)cnt * 8u, &vbar[st]);
         };
         if (tid == 0) {
             carry_slot[0] = 0.0;
@@ -360,11 +385,11 @@ __device__ __forceinline__ void gemv_phase_csr(Kst& k, const DenseCtx& c, const 
         auto gather_issue = [&](int t, double (&x)[kCsrE], long long& wv) {
             const Tile d = describe(t);
             const int st = t % kCsrStages;
-            if (tid <= d.nrows && tid < kCsrWin) wv = c.csr_ptr[d.r_cur + tid];     // consumed a step later (finish_products)
+            if (tid <= d.nrows && tid < kCsrWin) wv = csr_ptr[d.r_cur + tid];     // consumed a step later (finish_products)
             if (d.slow) return;
-            const int* idx = idx_ring + (size_t)st * kCsrTile;
-            mbar_wait(&ibar[st], (k.parbits >> st) & 1u);
-            k.parbits ^= 1u << st;
+            const SharedArr<int> idx = idx_sh + st * kCsrTile;
+            mbar_wait(&ibar[st], (parbits >> st) & 1u);
+            parbits ^= 1u << st;
             int j[kCsrE];
             if (d.cnt == kCsrTile) {
 #pragma unroll
@@ -374,24 +399,24 @@ __device__ __forceinline__ void gemv_phase_csr(Kst& k, const DenseCtx& c, const 
                 for (int u = 0; u < kCsrE; ++u) { const int q = u * kDenseThreads + tid; j[u] = q < d.cnt ? idx[q] : 0; }
             }
 #pragma unroll
-            for (int u = 0; u < kCsrE; ++u) x[u] = c.csr_l1 ? ld_ca(v + j[u]) : ld_cg(v + j[u]);
+            for (int u = 0; u < kCsrE; ++u) x[u] = csr_l1 ? ld_ca(v + j[u]) : ld_cg(v + j[u]);
         };
         // F(t): products of tile t in place over its values (the gather left two steps ago), row-pointer window of the tile
         auto finish_products = [&](int t, const double (&x)[kCsrE], long long wv) {
             const Tile d = describe(t);
             const int st = t % kCsrStages;
-            double* prod = val_ring + (size_t)st * kCsrTile;
+            const SharedArr<double> prod = val_sh + st * kCsrTile;
             if (tid <= d.nrows && tid < kCsrWin) win[(t & 1) * kCsrWin + tid] = rel(wv, (g0 + t) * kCsrTile, d);
             if (d.slow) {
                 const long long T = (g0 + t) * kCsrTile;
                 for (int q = tid; q < d.cnt; q += kDenseThreads) {
-                    const double xv = c.csr_l1 ? ld_ca(v + __ldg(c.csr_idx + T + q)) : ld_cg(v + __ldg(c.csr_idx + T + q));
-                    prod[q] = ldg_stream(c.csr_val + T + q) * xv;
+                    const double xv = csr_l1 ? ld_ca(v + __ldg(csr_idx + T + q)) : ld_cg(v + __ldg(csr_idx + T + q));
+                    prod[q] = ldg_stream(csr_val + T + q) * xv;
                 }
                 return;
             }
-            mbar_wait(&vbar[st], (k.parbits >> (kCsrStages + st)) & 1u);
-            k.parbits ^= 1u << (kCsrStages + st);
+            mbar_wait(&vbar[st], (parbits >> (kCsrStages + st)) & 1u);
+            parbits ^= 1u << (kCsrStages + st);
             if (d.cnt == kCsrTile) {
 #pragma unroll
                 for (int u = 0; u < kCsrE; ++u) prod[u * kDenseThreads + tid] *= x[u];
@@ -403,8 +428,8 @@ __device__ __forceinline__ void gemv_phase_csr(Kst& k, const DenseCtx& c, const 
         // R(t): the rows of tile t, summed from the products in shared memory
         auto row_sums = [&](int t) {
             const Tile cur = describe(t);
-            const int* pw = win + (t & 1) * kCsrWin;
-            const double* prod = val_ring + (size_t)(t % kCsrStages) * kCsrTile;
+            const SharedArr<int> pw = win + (t & 1) * kCsrWin;
+            const SharedArr<double> prod = val_sh + (t % kCsrStages) * kCsrTile;
             const double carry_in = carry_slot[t & 1];
             for (int kk = 0; kk * ngroups < cur.nrows; ++kk) {        // CTA-uniform trip count
                 if (warp_gid0 + kk * ngroups >= cur.nrows) continue;  // warp-uniform: nothing for this warp in this pass
@@ -414,7 +439,7 @@ __device__ __forceinline__ void gemv_phase_csr(Kst& k, const DenseCtx& c, const 
                 if (active) {
                     if (i + 1 < kDenseThreads) { p0 = pw[i]; p1 = pw[i + 1]; }      // the window holds the pointers of rows 0 .. threads-1
                                                                                        // (slot i is filled by thread i); beyond it: global loads
-                    else { const long long T = (g0 + t) * kCsrTile; p0 = rel(c.csr_ptr[r], T, cur); p1 = rel(c.csr_ptr[r + 1], T, cur); }
+                    else { const long long T = (g0 + t) * kCsrTile; p0 = rel(csr_ptr[r], T, cur); p1 = rel(csr_ptr[r + 1], T, cur); }
                 }
                 const bool complete = active && p1 <= cur.hi;         // the row ends inside this CTA's part of the tile
                 const int hi = p1 < cur.hi ? p1 : cur.hi;
@@ -432,7 +457,7 @@ __device__ __forceinline__ void gemv_phase_csr(Kst& k, const DenseCtx& c, const 
                 for (int o = G >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
                 if (glane == 0 && active) {
                     if (i == 0) acc = carry_in + acc;                 // earlier tiles' part of the row first
-                    if (complete) c.ytmp[r] = acc;                    // the epilogue runs after the tile loop, all rows side by side
+                    if (complete) ytmp[r] = acc;                    // the epilogue runs after the tile loop, all rows side by side
                     else carry_slot[(t + 1) & 1] = acc;               // the one row that continues into the next tile (the last one)
                 }
             }
@@ -467,19 +492,34 @@ __device__ __forceinline__ void gemv_phase_csr(Kst& k, const DenseCtx& c, const 
         }
         // epilogue pass: one row per thread at a time, so the loads an epilogue does (e.g. SPG's d_r for d.Ad) overlap across
         // rows instead of stalling the tile loop once per tile (the last step's barrier made the row sums visible to the CTA)
-        for (int r = cr0 + tid; r < cr1; r += kDenseThreads) epi(c.row0 + r, ld_cg(c.ytmp + r));
+        for (int r = cr0 + tid; r < cr1; r += kDenseThreads) epi(row0 + r, ld_cg(ytmp + r));
     } else {
-        for (int r = cr0 + tid; r < cr1; r += kDenseThreads) epi(c.row0 + r, 0.0);     // a range of empty rows
+        for (int r = cr0 + tid; r < cr1; r += kDenseThreads) epi(row0 + r, 0.0);     // a range of empty rows
     }
+    k.parbits = parbits;
     k.gemv += 1;
     __syncthreads();
 }
 
+// The CSR phase as a function of its own: for a solver program whose live state does not fit next to the tile loop's
+// registers (MPRGP: the inlined phase spilled inside the loop) the call gives the loop its own register allocation; the
+// caller's state is saved once around the call instead of being spilled and reloaded in every step.
+template <class Epi>
+__device__ __noinline__ void gemv_phase_csr_outlined(Kst& k, const DenseCtx& c, const double* v, Epi epi) {
+    gemv_phase_csr(k, c, v, epi);
+}
+
 // y_row = sum_j A[row][j] v[j] for the rows of this CTA; epi(row, y_row) is called once per row.
 // v: full-length global vector (npad entries, zero tail), complete before the phase starts.
-template <class Epi>
+template <bool kOutlineCsr = false, class Epi>
 __device__ __forceinline__ void gemv_phase(Kst& k, const DenseCtx& c, const double* v, Epi epi) {
-    if constexpr (!CCQP_DENSE_ONLY) { if (CCQP_CSR_ONLY || c.csr_val) { gemv_phase_csr(k, c, v, epi); return; } }
+    if constexpr (!CCQP_DENSE_ONLY) {
+        if (CCQP_CSR_ONLY || c.csr_val) {
+            if constexpr (kOutlineCsr && CCQP_CSR_ONLY) gemv_phase_csr_outlined(k, c, v, epi);
+            else gemv_phase_csr(k, c, v, epi);
+            return;
+        }
+    }
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = c.n, CW = c.CW, SW = c.SW, np = c.np, nseg = c.nseg;
     const int nrows_cta = k.r1 - k.r0;
@@ -938,10 +978,10 @@ static __device__ unsigned long long bisect_mask(Kst& k, const DenseCtx& c, cons
 // y = epi(r, (A vin)_r) for this rank's rows, complete in `dst` on every rank when the call
 // returns.  Sharded solves go through the output pool and copy (see the top of this section);
 // a single GPU writes dst directly.  Ends with a barrier.
-template <class Epi>
+template <bool kOutlineCsr = false, class Epi>
 __device__ __forceinline__ void gemv_into(Kst& k, const DenseCtx& c, const double* vin, double* dst, Epi epi) {
     double* y = (c.x.world > 1) ? next_y(k, c) : dst;
-    gemv_phase(k, c, vin, [&](int r, double s) { pub_store(c, y, r, epi(r, s)); });
+    gemv_phase<kOutlineCsr>(k, c, vin, [&](int r, double s) { pub_store(c, y, r, epi(r, s)); });
     barrier_only<true>(k, c);
     if (y != dst) {
         CCQP_ELEMS(i) dst[i] = ld_cg(y + i);
@@ -958,7 +998,7 @@ static __device__ void solve_mprgp(Kst& k, const DenseCtx& c) {
     project_pass(c.T, k.gtid, k.gstride, k.sm.scratch, [&](int i) { return c.x0[i]; },
                  [&](int i, double, double pr) { xk[i] = pr; xn[i] = pr; });
     barrier_only<false>(k, c);
-    gemv_into(k, c, xk, gk, [&](int r, double s) { return s + b[r]; });
+    gemv_into<true>(k, c, xk, gk, [&](int r, double s) { return s + b[r]; });
     k.mv = 1;
     CCQP_ELEMS(i) gn[i] = ld_cg(gk + i);
     double a1[1] = {residual_partial(k, c, cs, [&](int i) { return ld_cg(xk + i); }, [&](int i) { return ld_cg(gk + i); })};
@@ -966,7 +1006,7 @@ static __device__ void solve_mprgp(Kst& k, const DenseCtx& c) {
     double res = sqrt(a1[0]);
     if (res >= c.tol) {
         double a2[2] = {0.0, 0.0};
-        gemv_phase(k, c, gk, [&](int r, double s) { const double gr = ld_cg(gk + r); a2[0] = fma(gr, s, a2[0]); a2[1] = fma(gr, gr, a2[1]); });
+        gemv_phase<true>(k, c, gk, [&](int r, double s) { const double gr = ld_cg(gk + r); a2[0] = fma(gr, s, a2[0]); a2[1] = fma(gr, gr, a2[1]); });
         k.mv += 1;                                   // counted (:1077-1078)
         reduce_sync<2, true>(k, c, a2);
         double abb = a2[1] / a2[0];
@@ -976,7 +1016,7 @@ static __device__ void solve_mprgp(Kst& k, const DenseCtx& c) {
         barrier_only<false>(k, c);
         for (;;) {
             dbg_stamp(c, k.iters, 0);
-            gemv_into(k, c, xk, gk, [&](int r, double s) { return s + b[r]; });
+            gemv_into<true>(k, c, xk, gk, [&](int r, double s) { return s + b[r]; });
             k.mv += 1;
             dbg_stamp(c, k.iters, 1);
             if (hit_max(k, c)) break;
@@ -1016,7 +1056,7 @@ static __device__ void solve_mprgp(Kst& k, const DenseCtx& c) {
                 double s1[1] = {0.0};
                 {
                     double* y = (c.x.world > 1) ? next_y(k, c) : Ap;
-                    gemv_phase(k, c, p, [&](int r, double s) { pub_store(c, y, r, s); s1[0] = fma(ld_cg(p + r), s, s1[0]); });
+                    gemv_phase<true>(k, c, p, [&](int r, double s) { pub_store(c, y, r, s); s1[0] = fma(ld_cg(p + r), s, s1[0]); });
                     k.mv += 1;
                     reduce_sync<1, true>(k, c, s1);
                     if (y != Ap) {
@@ -1072,7 +1112,7 @@ static __device__ void solve_mprgp(Kst& k, const DenseCtx& c) {
                                  [&](int i, double, double pr) { xn[i] = pr; });
                     barrier_only<false>(k, c);
                     dbg_stamp(c, k.iters, 5);
-                    gemv_into(k, c, xn, gn, [&](int r, double s) { return s + b[r]; });
+                    gemv_into<true>(k, c, xn, gn, [&](int r, double s) { return s + b[r]; });
                     k.mv += 1;
                     dbg_stamp(c, k.iters, 6);
                     if (hit_max(k, c)) break;
@@ -1088,7 +1128,7 @@ static __device__ void solve_mprgp(Kst& k, const DenseCtx& c) {
                     CCQP_ELEMS(i) { const double dv = ld_cg(xk + i) - ld_cg(xn + i); w[i] = dv; s1[0] = fma(dv, dv, s1[0]); }
                     reduce_sync<1, false>(k, c, s1);
                     double s2[1] = {0.0};
-                    gemv_phase(k, c, w, [&](int r, double s) { s2[0] = fma(ld_cg(w + r), s, s2[0]); });
+                    gemv_phase<true>(k, c, w, [&](int r, double s) { s2[0] = fma(ld_cg(w + r), s, s2[0]); });
                     reduce_sync<1, true>(k, c, s2);
                     abb = s1[0] / (s2[0] + 10 * kEps);
                 }
