@@ -289,6 +289,7 @@ def bench_batched(device, steps, warmup, batch=None, seed=1, reduce_max=None):
         e = min(local, s + chunk)
         G = torch.randn((e - s, NB, NB), generator=g, device=device, dtype=torch.float64)
         A[s:e] = G @ G.transpose(1, 2) / NB + torch.eye(NB, device=device, dtype=torch.float64)
+        A[s:e] = 0.5 * (A[s:e] + A[s:e].transpose(1, 2))        # exactly symmetric (the `_sym` rows read the upper block triangle only)
         xs = 1 - 4 * torch.rand((e - s, NB), generator=g, device=device, dtype=torch.float64)
         b[s:e] = -(A[s:e] @ xs.unsqueeze(-1)).squeeze(-1)
     lb, ub = -torch.ones_like(b), torch.ones_like(b)
@@ -297,12 +298,15 @@ def bench_batched(device, steps, warmup, batch=None, seed=1, reduce_max=None):
     peak, _ = measured_peak()
     fpk = fp64_peak(device.index or 0)
     ranks = 1
-    for name, cls in (("BBPGD", solvers.CCQPSolverBBPGD), ("SPG", solvers.CCQPSolverSPG)):
+    # `X`: ccqp_solve_batched (any A, one CTA of 64 threads per problem); `X_sym`: ccqp_solve_batched_sym (the caller declares A
+    # symmetric; one warp per problem, upper block triangle only) -- same problems, same tolerance
+    for name, cls, sym in (("BBPGD", solvers.CCQPSolverBBPGD, False), ("SPG", solvers.CCQPSolverSPG, False),
+                           ("BBPGD_sym", solvers.CCQPSolverBBPGD, True), ("SPG_sym", solvers.CCQPSolverSPG, True)):
         s = cls(1e-8, 5000)
         s.quiet = True
         times = []
         for it in range(warmup + steps):
-            s.solve_batched(A, b, lb, ub, uniforms=uni)
+            s.solve_batched(A, b, lb, ub, uniforms=uni, symmetric=sym)
             if it >= warmup:
                 times.append(s.solution_gpu_time)
         t = float(np.mean(times))

@@ -24,7 +24,7 @@ EXPORTS = ["ccqp_abi_version", "ccqp_status_string", "ccqp_last_error", "ccqp_cr
            "ccqp_set_stream", "ccqp_get_info", "ccqp_set_matrix", "ccqp_set_matrix_csr", "ccqp_set_projection", "ccqp_solve", "ccqp_solve_async", "ccqp_solve_wait",
            "ccqp_solve_batched", "ccqp_gemv", "ccqp_gemv_timed", "ccqp_project", "ccqp_normal", "ccqp_comm_export",
            "ccqp_comm_attach", "ccqp_comm_prepare", "ccqp_comm_detach", "ccqp_debug_divide", "ccqp_fp64_peak",
-           "ccqp_microbench", "ccqp_debug_emulate_ranks", "ccqp_debug_solve_emulated", "ccqp_projected_gradient", "ccqp_solve_batched_table"]
+           "ccqp_microbench", "ccqp_debug_emulate_ranks", "ccqp_debug_solve_emulated", "ccqp_projected_gradient", "ccqp_solve_batched_table", "ccqp_solve_batched_sym"]
 
 
 class Block(C.Structure):
@@ -81,6 +81,7 @@ def load():
     lib.ccqp_solve_wait.argtypes = [vp, C.POINTER(Result)]
     lib.ccqp_solve_batched.argtypes = [vp, i32, C.POINTER(Params), i64, i64, dp, dp, dp, dp, dp, dp, i64, dp, i32,
                                        C.POINTER(Result), C.POINTER(Result)]
+    lib.ccqp_solve_batched_sym.argtypes = lib.ccqp_solve_batched.argtypes
     lib.ccqp_solve_batched_table.argtypes = [vp, i32, C.POINTER(Params), i64, i64, dp, dp, dp, C.POINTER(Block), i64, dp, i64, dp, i64,
                                              dp, i32, C.POINTER(Result), C.POINTER(Result)]
     lib.ccqp_gemv.argtypes = [vp, dp, dp, i32]

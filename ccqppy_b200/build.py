@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libccqp_b200.so")
-SOURCES = ["capi.cu", "batched.cu", "emu.cu", "csr.cu"]      # separate translation units only so that they compile in parallel
+SOURCES = ["capi.cu", "batched.cu", "batched_sym.cu", "emu.cu", "csr.cu"]      # separate translation units only so that they compile in parallel
 HEADERS = ["common.cuh", "proj.cuh", "dense.cuh", "batched.cuh", "microbench.cuh", "internal.h",
            os.path.join("..", "..", "include", "ccqp_b200.h")]
 

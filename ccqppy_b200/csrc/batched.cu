@@ -8,8 +8,8 @@ int batched_solve_entry(cudaStream_t stream, int sm_count, int solver, const ccq
                         const double* A, const double* b, const double* x0, const double* lb, const double* ub,
                         const double* uniforms, long long n_uniforms, double* x_out, int memtype, ccqp_result* results,
                         ccqp_result* summary, cudaEvent_t ev0, cudaEvent_t ev1, int* launches, std::string& err,
-                        const std::function<void*(size_t)>& alloc) {
-    return batched_solve(stream, sm_count, nullptr, 0, solver, prm, batch, n, A, b, x0, lb, ub, uniforms, n_uniforms, x_out,
+                        const std::function<void*(size_t)>& alloc, bool symmetric) {
+    return batched_solve(stream, sm_count, nullptr, symmetric, solver, prm, batch, n, A, b, x0, lb, ub, uniforms, n_uniforms, x_out,
                          memtype, results, summary, ev0, ev1, launches, err, alloc);
 }
 
@@ -49,7 +49,7 @@ int batched_solve_table_entry(cudaStream_t stream, int sm_count, int solver, con
         at += bl.dim;
     }
     if (at != n) return CCQP_ERR_INVALID_ARG;
-    return batched_solve(stream, sm_count, &tab, 0, solver, prm, batch, n, A, b, x0, nullptr, nullptr, uniforms, n_uniforms, x_out,
+    return batched_solve(stream, sm_count, &tab, false, solver, prm, batch, n, A, b, x0, nullptr, nullptr, uniforms, n_uniforms, x_out,
                          memtype, results, summary, ev0, ev1, launches, err, alloc);
 }
 

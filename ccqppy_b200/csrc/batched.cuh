@@ -836,6 +836,7 @@ inline double sqrt_threshold(double tol, bool strict) {
     return out;
 }
 
+#ifndef CCQP_BATCHED_DEVICE_ONLY        // batched_sym.cu shares the context / helpers above, not the launchers below
 template <int SOLVER, bool WREG, bool GEN, int NT>
 inline cudaError_t launch_batched_nt(const BatchedCtx& c, int sm_count, cudaStream_t stream) {
     int per_sm = 0;
@@ -868,9 +869,15 @@ struct BatchedTable {
     int has_norm = 0;
 };
 
+// batched_sym.cu: the one-warp-per-problem kernels for symmetric Hessians (n <= 64; PGD / BBPGD / BBPGDf / SPG, Box per problem)
+bool batched_sym_supported(int solver, long long n);
+cudaError_t launch_batched_sym(const BatchedCtx& c, int solver, bool wreg, int sm_count, cudaStream_t stream);
+
 // Returns a ccqp_status.  `alloc(bytes)` returns a device workspace of at least that size.
 // tab != nullptr: the general table replaces the per-problem Box (lb / ub are ignored).
-inline int batched_solve(cudaStream_t stream, int sm_count, const BatchedTable* tab, size_t, int solver, const ccqp_params& prm,
+// sym: the caller declares every A[i] symmetric (ccqp_solve_batched_sym); where batched_sym_supported() the upper block triangle
+// alone is read, otherwise the general kernels run (same answer for a symmetric A).
+inline int batched_solve(cudaStream_t stream, int sm_count, const BatchedTable* tab, bool sym, int solver, const ccqp_params& prm,
                          long long batch, long long n, const double* A, const double* b, const double* x0,
                          const double* lb, const double* ub, const double* uniforms, long long n_uniforms, double* x_out,
                          int memtype, ccqp_result* results, ccqp_result* summary, cudaEvent_t ev0, cudaEvent_t ev1,
@@ -949,7 +956,9 @@ inline int batched_solve(cudaStream_t stream, int sm_count, const BatchedTable* 
     BCU(cudaEventRecord(ev0, stream));
     cudaError_t le;
     const bool wreg = prm.m == kBWinReg;
-    if (tab) switch (solver) {
+    const bool use_sym = sym && !tab && batched_sym_supported(solver, n);
+    if (use_sym) le = launch_batched_sym(c, solver, wreg, sm_count, stream);
+    else if (tab) switch (solver) {
         case CCQP_SOLVER_PGD: le = launch_batched<CCQP_SOLVER_PGD, true, true>(c, sm_count, stream); break;
         case CCQP_SOLVER_APGD: le = launch_batched<CCQP_SOLVER_APGD, true, true>(c, sm_count, stream); break;
         case CCQP_SOLVER_APGD_AR: le = launch_batched<CCQP_SOLVER_APGD_AR, true, true>(c, sm_count, stream); break;
@@ -985,6 +994,8 @@ inline int batched_solve(cudaStream_t stream, int sm_count, const BatchedTable* 
     BCU(cudaEventElapsedTime(&ms, ev0, ev1));
     long long tot_mv = 0, tot_gemv = 0, tot_it = 0, tot_dr = 0, nconv = 0;
     int first_status = 0;
+    double hbmA = 8.0 * n * n;                  // bytes of A[i] the kernel reads
+    if (use_sym) { hbmA = 0; for (long long i = 0; i < n; ++i) hbmA += 8.0 * (double)(n - 8 * (i / 8)); }
     for (long long i = 0; i < batch; ++i) {
         const BatchedOut& o = hout[(size_t)i];
         if (results) {
@@ -992,7 +1003,7 @@ inline int batched_solve(cudaStream_t stream, int sm_count, const BatchedTable* 
             std::memset(&r, 0, sizeof(r));
             r.residual = o.residual; r.mv_count = o.mv; r.gemv_count = o.gemv; r.iterations = o.iters;
             r.uniforms_used = o.draws; r.converged = o.converged; r.status = o.status;
-            r.hbm_bytes = 8.0 * n * n + 8.0 * n * (x0 ? 5 : 4);
+            r.hbm_bytes = hbmA + 8.0 * n * (x0 ? 5 : 4);
         }
         tot_mv += o.mv; tot_gemv += o.gemv; tot_it += o.iters; tot_dr += o.draws; nconv += o.converged;
         if (o.status && !first_status) first_status = o.status;
@@ -1003,12 +1014,13 @@ inline int batched_solve(cudaStream_t stream, int sm_count, const BatchedTable* 
         summary->mv_count = tot_mv; summary->gemv_count = tot_gemv; summary->iterations = tot_it;
         summary->uniforms_used = tot_dr; summary->converged = (nconv == batch) ? 1 : 0;
         summary->status = first_status;
-        summary->hbm_bytes = (double)batch * (8.0 * n * n + 8.0 * n * (x0 ? 5 : 4)) + 8.0 * (double)tot_dr;
+        summary->hbm_bytes = (double)batch * (hbmA + 8.0 * n * (x0 ? 5 : 4)) + 8.0 * (double)tot_dr;
         summary->kernel_launches = 1;
         summary->residual = NAN;
     }
     return CCQP_OK;
 #undef BCU
 }
+#endif  // CCQP_BATCHED_DEVICE_ONLY
 
 }  // namespace ccqp

@@ -755,7 +755,7 @@ ccqp_status ccqp_projected_gradient(ccqp_handle* h, const double* x, const doubl
     return CCQP_OK;
 }
 
-ccqp_status ccqp_solve_batched(ccqp_handle* h, int solver, const ccqp_params* params, int64_t batch, int64_t n,
+static ccqp_status solve_batched_box(ccqp_handle* h, bool symmetric, int solver, const ccqp_params* params, int64_t batch, int64_t n,
                                const double* A, const double* b, const double* x0, const double* lb, const double* ub,
                                const double* uniforms, int64_t n_uniforms, double* x_out, int memtype,
                                ccqp_result* results, ccqp_result* summary) {
@@ -767,10 +767,25 @@ ccqp_status ccqp_solve_batched(ccqp_handle* h, int solver, const ccqp_params* pa
     ccqp_status st = (ccqp_status)batched_solve_entry(h->stream, h->sm_count, solver, *params,
                                                 batch, n, A, b, x0, lb, ub, uniforms, n_uniforms, x_out, memtype, results,
                                                 summary, h->ev0, h->ev1, &launches, err,
-                                                [&](size_t bytes) -> void* { return h->batched_ws.ensure(bytes) == cudaSuccess ? h->batched_ws.p : nullptr; });
+                                                [&](size_t bytes) -> void* { return h->batched_ws.ensure(bytes) == cudaSuccess ? h->batched_ws.p : nullptr; },
+                                                symmetric);
     h->launches += launches;
     if (st == CCQP_ERR_CUDA) h->last_error = err;
     return st;
+}
+
+ccqp_status ccqp_solve_batched(ccqp_handle* h, int solver, const ccqp_params* params, int64_t batch, int64_t n,
+                               const double* A, const double* b, const double* x0, const double* lb, const double* ub,
+                               const double* uniforms, int64_t n_uniforms, double* x_out, int memtype,
+                               ccqp_result* results, ccqp_result* summary) {
+    return solve_batched_box(h, false, solver, params, batch, n, A, b, x0, lb, ub, uniforms, n_uniforms, x_out, memtype, results, summary);
+}
+
+ccqp_status ccqp_solve_batched_sym(ccqp_handle* h, int solver, const ccqp_params* params, int64_t batch, int64_t n,
+                                   const double* A, const double* b, const double* x0, const double* lb, const double* ub,
+                                   const double* uniforms, int64_t n_uniforms, double* x_out, int memtype,
+                                   ccqp_result* results, ccqp_result* summary) {
+    return solve_batched_box(h, true, solver, params, batch, n, A, b, x0, lb, ub, uniforms, n_uniforms, x_out, memtype, results, summary);
 }
 
 ccqp_status ccqp_solve_batched_table(ccqp_handle* h, int solver, const ccqp_params* params, int64_t batch, int64_t n,

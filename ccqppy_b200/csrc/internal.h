@@ -13,12 +13,12 @@ namespace ccqp {
 
 struct DenseCtx;
 
-// batched.cu -- returns a ccqp_status; `alloc(bytes)` returns a device workspace of at least that size
+// batched.cu (+ batched_sym.cu: the kernels behind `symmetric`) -- returns a ccqp_status; `alloc(bytes)` returns a device workspace of at least that size
 int batched_solve_entry(cudaStream_t stream, int sm_count, int solver, const ccqp_params& prm, long long batch, long long n,
                         const double* A, const double* b, const double* x0, const double* lb, const double* ub,
                         const double* uniforms, long long n_uniforms, double* x_out, int memtype, ccqp_result* results,
                         ccqp_result* summary, cudaEvent_t ev0, cudaEvent_t ev1, int* launches, std::string& err,
-                        const std::function<void*(size_t)>& alloc);
+                        const std::function<void*(size_t)>& alloc, bool symmetric = false);
 
 // the same with ONE projection table (any block kinds) shared by all problems of the batch instead of a Box per problem
 int batched_solve_table_entry(cudaStream_t stream, int sm_count, int solver, const ccqp_params& prm, long long batch, long long n,

@@ -238,7 +238,7 @@ class CCQPSolverBase(ABC):
         return max(1, int(min(mx, cap))) if np.isfinite(mx) else min(cap, 4096)
 
     def solve_batched(self, A, b, lower_bound=None, upper_bound=None, x0=None, seeds=None, uniforms=None, n_uniforms=None,
-                      device=-1, convex_proj_op=None):
+                      device=-1, convex_proj_op=None, symmetric=False):
         """Extension: solve `batch` independent constrained QPs in one persistent kernel.
 
         Either per-problem boxes (`lower_bound` / `upper_bound` [batch, n]) or ONE operator of
@@ -252,7 +252,12 @@ class CCQPSolverBase(ABC):
         or `uniforms` [batch, K].  Results are per-problem arrays on the `solution*` properties;
         `solution_status` holds the per-problem ccqp_status raised inside the kernel.  A problem whose
         SPG step bound is NaN raises OverflowError (np.random.uniform does, solvers.py:959); a problem
-        that used up its uniform stream raises CCQPError naming the problems (pass more samples)."""
+        that used up its uniform stream raises CCQPError naming the problems (pass more samples).
+
+        `symmetric=True` declares every A[i] symmetric (what the reference's objective assumes): with per-problem
+        boxes, n <= 64 and PGD / BBPGD / BBPGDf / SPG the one-warp-per-problem kernels then read only the upper block
+        triangle of A[i] (entries [r][c] with c >= 8 * (r // 8); `ccqp_solve_batched_sym`); every other case runs the
+        general kernels.  The caller vouches for the symmetry: it is not checked."""
         time_start = time.time()
         if not self.quiet:
             print("solving " + self._label)
@@ -311,9 +316,10 @@ class CCQPSolverBase(ABC):
                                               ptrs[2][0], blocks.ptr, len(blocks), pp, params.size, ptrs[5][0], K,
                                               ptrs[6][0], mem, results, ctypes.byref(summary))
         else:
-            st = lib.ccqp_solve_batched(h.h, self._solver_id, ctypes.byref(prm), batch, n, ptrs[0][0], ptrs[1][0],
-                                        ptrs[2][0], ptrs[3][0], ptrs[4][0], ptrs[5][0], K, ptrs[6][0], mem, results,
-                                        ctypes.byref(summary))
+            entry = lib.ccqp_solve_batched_sym if symmetric else lib.ccqp_solve_batched
+            st = entry(h.h, self._solver_id, ctypes.byref(prm), batch, n, ptrs[0][0], ptrs[1][0],
+                       ptrs[2][0], ptrs[3][0], ptrs[4][0], ptrs[5][0], K, ptrs[6][0], mem, results,
+                       ctypes.byref(summary))
         _capi.check(h.h, st)
         rec = np.frombuffer(results, dtype=np.dtype([("residual", "f8"), ("gpu_seconds", "f8"), ("hbm_bytes", "f8"),
                                                      ("mv", "i8"), ("gemv", "i8"), ("it", "i8"), ("draws", "i8"),

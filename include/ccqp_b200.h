@@ -183,6 +183,19 @@ ccqp_status ccqp_solve_batched(ccqp_handle* h, int solver, const ccqp_params* pa
                                int64_t n_uniforms, double* x_out, int memtype,
                                ccqp_result* results, ccqp_result* summary);
 
+/* The same for a caller that declares every A[i] SYMMETRIC (the reference's objective 0.5 x'Ax + b'x has the gradient Ax + b
+ * its solvers iterate with, solvers.py:133, only for such an A).  Where the one-warp-per-problem kernels apply -- n <= 64 and
+ * solver PGD / BBPGD / BBPGDf / SPG -- only the upper block triangle of A[i] is read: entries A[i][r][c] with c >= 8 * (r / 8),
+ * the dsymv('U') contract at 8 x 8 granularity; the blocks below are never touched (18 KB instead of 32 KB of HBM traffic per
+ * problem at n = 64, eight problems in flight per SM instead of six).  Every other case runs ccqp_solve_batched's kernels
+ * on the full matrix -- the same answer for a symmetric A.  Results equal ccqp_solve_batched's up to the summation order of
+ * the mat-vec (last-bit differences). */
+ccqp_status ccqp_solve_batched_sym(ccqp_handle* h, int solver, const ccqp_params* params, int64_t batch,
+                                   int64_t n, const double* A, const double* b, const double* x0,
+                                   const double* lb, const double* ub, const double* uniforms,
+                                   int64_t n_uniforms, double* x_out, int memtype,
+                                   ccqp_result* results, ccqp_result* summary);
+
 /* The same with ONE feasible set shared by all problems of the batch, given as a block table (any block kinds:
  * DisjointProjOp of Box / Lower / Upper / Identity / Sphere / reference Cone / SOC leaves, solution_spaces.py:77-560) --
  * the contact-style case: every problem has the same friction-disc structure.  Problem i equals

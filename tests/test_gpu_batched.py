@@ -244,3 +244,96 @@ def test_batched_n128_shared_table_and_limit():
         assert np.linalg.norm(s.solution[i] - o["solution"]) <= 1e-9 * np.linalg.norm(o["solution"])
     with pytest.raises(_capi.CCQPError):            # beyond the batched mode: use solve()
         make_solver(pr.BBPGD, 1e-8, 100).solve_batched(np.zeros((2, 129, 129)), np.zeros((2, 129)), np.zeros((2, 129)), np.ones((2, 129)))
+
+
+# ---- symmetric Hessians: one warp per problem, upper block triangle only (ccqp_solve_batched_sym, csrc/batched_sym.cu) ----
+def make_sym_batch(batch, n, seed0=0, mu=1.0):
+    A, b, lb, ub = make_batch(batch, n, seed0, mu)
+    A = 0.5 * (A + A.transpose(0, 2, 1))        # exactly symmetric, whatever the BLAS behind G @ G.T does
+    return A, b, lb, ub
+
+
+@pytest.mark.parametrize("solver", [pr.PGD, pr.BBPGD, pr.BBPGDF, pr.SPG])
+@pytest.mark.parametrize("n", [64, 62, 32, 17, 8, 5])
+def test_batched_symmetric_matches_oracle(solver, n):
+    """Even n runs the TMA-staged tile, odd n the direct loads; n = 32 starts from a non-zero x0.  Same acceptance as
+    test_batched_matches_oracle (the summation order of the mat-vec differs from NumPy's, so a data-dependent
+    branch may flip on a rounding-level difference in a few problems)."""
+    batch, max_mv, step, K = 48, 5000, 0.1, 512
+    A, b, lb, ub = make_sym_batch(batch, n, seed0=300)
+    x0 = None if n != 32 else 0.5 * np.random.default_rng(3).standard_normal((batch, n))
+    s = make_solver(solver, 1e-8, max_mv, step)
+    s.solve_batched(A, b, lb, ub, x0=x0, seeds=np.arange(batch), n_uniforms=K, symmetric=True)
+    same = 0
+    for i in range(batch):
+        o = oracle_one(solver, A[i], b[i], lb[i], ub[i], None if x0 is None else x0[i], 1e-8, max_mv, step, i, K)
+        assert bool(s.solution_converged[i]) == o["converged"]
+        mv = int(s.solution_num_matrix_vector_multiplications[i])
+        scale = max(np.linalg.norm(o["solution"]), 1e-300)
+        if mv == o["mv"]:
+            same += 1
+            assert np.linalg.norm(s.solution[i] - o["solution"]) <= 1e-9 * scale
+            assert abs(s.solution_residual[i] - o["residual"]) <= 1e-6 * o["residual"] + 1e-14
+        else:
+            assert abs(mv - o["mv"]) <= max(2, round(0.1 * o["mv"])), (i, mv, o["mv"])
+            assert np.linalg.norm(s.solution[i] - o["solution"]) <= 1e-5 * scale
+    assert same >= 0.9 * batch, (same, batch)
+
+
+@pytest.mark.parametrize("n", [64, 40, 17])
+def test_batched_symmetric_reads_upper_block_triangle_only(n):
+    """The contract of ccqp_solve_batched_sym: entries [r][c] with c < 8 * (r // 8) are never read -- poisoned with NaN they
+    change nothing, bit for bit; the general kernels agree with it to rounding; unsupported solvers fall back to them."""
+    import torch
+    batch = 200
+    A, b, lb, ub = make_sym_batch(batch, n, seed0=500)
+    poisoned = A.copy()
+    rr, cc = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
+    poisoned[:, cc < 8 * (rr // 8)] = np.nan
+    for solver in (pr.BBPGD, pr.SPG):
+        clean = make_solver(solver, 1e-8, 5000).solve_batched(A, b, lb, ub, seeds=np.arange(batch), n_uniforms=400, symmetric=True)
+        pois = make_solver(solver, 1e-8, 5000).solve_batched(poisoned, b, lb, ub, seeds=np.arange(batch), n_uniforms=400, symmetric=True)
+        assert np.array_equal(clean.solution, pois.solution)
+        assert np.array_equal(clean.solution_num_matrix_vector_multiplications, pois.solution_num_matrix_vector_multiplications)
+        assert clean.solution_converged.all()
+        full = make_solver(solver, 1e-8, 5000).solve_batched(A, b, lb, ub, seeds=np.arange(batch), n_uniforms=400)
+        assert np.abs(clean.solution - full.solution).max() <= 1e-6
+        assert (clean.solution_num_matrix_vector_multiplications == full.solution_num_matrix_vector_multiplications).mean() >= 0.9
+        dev = make_solver(solver, 1e-8, 5000).solve_batched(torch.from_numpy(A).cuda(), torch.from_numpy(b).cuda(),
+                                                          torch.from_numpy(lb).cuda(), torch.from_numpy(ub).cuda(),
+                                                          seeds=np.arange(batch), n_uniforms=400, symmetric=True)
+        assert np.array_equal(dev.solution.cpu().numpy(), clean.solution)
+    # APGD / MPRGP have no symmetric kernel: the flag is accepted and the general kernels run
+    for solver in (pr.APGD, pr.MPRGP):
+        a1 = make_solver(solver, 1e-6, 5000).solve_batched(A[:16], b[:16], lb[:16], ub[:16], symmetric=True)
+        a2 = make_solver(solver, 1e-6, 5000).solve_batched(A[:16], b[:16], lb[:16], ub[:16])
+        assert np.array_equal(a1.solution, a2.solution)
+
+
+def test_batched_symmetric_large_properties():
+    """More problems than one wave of warps: converged, feasible, fixed point of the projected-gradient map; a permuted
+    batch gives permuted, bit-identical answers (the work queue does not leak into the results)."""
+    import torch
+    batch, n, tol = 20000, 64, 1e-8
+    g = torch.Generator(device="cuda").manual_seed(0)
+    G = torch.randn((batch, n, n), generator=g, device="cuda", dtype=torch.float64)
+    A = G @ G.transpose(1, 2) / n + torch.eye(n, device="cuda", dtype=torch.float64)
+    A = 0.5 * (A + A.transpose(1, 2))
+    xs = 1 - 4 * torch.rand((batch, n), generator=g, device="cuda", dtype=torch.float64)
+    b = -(A @ xs.unsqueeze(-1)).squeeze(-1)
+    lb, ub = -torch.ones_like(b), torch.ones_like(b)
+    for solver in (pr.BBPGD, pr.SPG):
+        s = make_solver(solver, tol, 5000).solve_batched(A, b, lb, ub, n_uniforms=256, symmetric=True)
+        x = s.solution
+        assert s.solution_converged.all()
+        assert bool(((x >= lb) & (x <= ub)).all())
+        grad = (A @ x.unsqueeze(-1)).squeeze(-1) + b
+        if solver == pr.BBPGD:
+            res = (x - torch.clamp(x - 1e-6 * grad, lb, ub)).norm(dim=1) / (3 * n * 1e-6)
+            assert float(res.max()) < tol * 1.001
+        else:
+            assert float((torch.clamp(x - 0.25 * grad, lb, ub) - x).norm(dim=1).max()) < 1e-7
+    perm = torch.randperm(batch, device="cuda")
+    s1 = make_solver(pr.BBPGD, tol, 5000).solve_batched(A, b, lb, ub, symmetric=True)
+    s2 = make_solver(pr.BBPGD, tol, 5000).solve_batched(A[perm].contiguous(), b[perm].contiguous(), lb, ub, symmetric=True)
+    assert torch.equal(s1.solution[perm], s2.solution)
