@@ -150,7 +150,8 @@ class Handle:
 
     PROBES = ("dfma", "dadd", "dmul", "shfl64_dadd", "div_dadd", "sqrt_dadd", "lds128_bcast_dadd", "lds128_distinct_dadd",
               "sts_bar_lds_dadd_bar", "bar64", "dsetp_sel_dadd", "dmma884_dependent", "dmma884_x8_independent_plus_8_dadd",
-              "warpsum_dmma_dadd_dmma", "warpsum_5_shfl64_dadd", "dmma_x8_with_dfma_x8")
+              "warpsum_dmma_dadd_dmma", "warpsum_5_shfl64_dadd", "dmma_x8_with_dfma_x8",
+              "dfma_independent_x8_one_fresh_operand", "dfma_independent_x8_two_fresh_operands", "dfma_matvec_8x8_register_block")
 
     def microbench(self):
         """SM cycles per dependent operation (ccqp_microbench), as a dict."""

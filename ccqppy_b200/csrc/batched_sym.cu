@@ -48,6 +48,7 @@ static_assert(kTile == 2432, "compact tile");
 struct Smem {
     double tile[kTile];             // the NEXT problem: upper block triangle, row by row
     double vstage[3][kN];           // ... its b / lb / ub
+    double vcur[3][kN];             // b / lb / ub of the problem being solved (12 registers per lane that the mat-vec needs more)
     double xs[kXS];                 // mat-vec input
     double ct[kSlots * kCtPitch];   // partial sums of the mat-vec
     uint64_t mbar;
@@ -120,7 +121,21 @@ struct Lane {                   // shared-window addresses of this lane, fixed f
 };
 
 // y = A v for the two unknowns of the lane.  a: the off-diagonal block (r, c); dg: rows 2l, 2l+1 of the diagonal block.
-__device__ __forceinline__ V2 matvec(const double (&a)[8][8], const double (&dg)[2][8], const Lane& L, V2 v) {
+#ifdef CCQP_BSYM_TIMING
+struct MvT { long long t[6]; };
+__device__ MvT g_mvt_dummy;
+#define MVT_AT(k) if (mt) mt->t[k] += clock64() - t_in
+#else
+#define MVT_AT(k)
+#endif
+__device__ __forceinline__ V2 matvec(const double (&a)[8][8], const double (&dg)[2][8], const Lane& L, V2 v
+#ifdef CCQP_BSYM_TIMING
+                                     , MvT* mt = nullptr
+#endif
+) {
+#ifdef CCQP_BSYM_TIMING
+    const long long t_in = clock64();
+#endif
     // padding (index >= n) is published as an exact zero whatever v is (batched.cuh matvec)
     sts_f64x2(L.xs_wr, L.act0 ? v.a : 0.0, L.act1 ? v.b : 0.0);
     __syncwarp();
@@ -137,6 +152,7 @@ __device__ __forceinline__ V2 matvec(const double (&a)[8][8], const double (&dg)
         d10 = fma(dg[1][j], xd[j], d10); d11 = fma(dg[1][j + 4], xd[j + 4], d11);
     }
     d00 += d01; d10 += d11;
+    MVT_AT(0);
     // s1[i] = sum_j a[i][j] x_c[j], four rows (= four independent chains: DFMA latency 8 cycles, issue 2) at a time
 #pragma unroll
     for (int h = 0; h < 8; h += 4) {
@@ -153,6 +169,7 @@ __device__ __forceinline__ V2 matvec(const double (&a)[8][8], const double (&dg)
             for (int j = 0; j < 8; j += 2) lds_f64x2(L.xs_r + j * 8, xr[j], xr[j + 1]);
         }
     }
+    MVT_AT(1);
     // s2[j] = sum_i a[i][j] x_r[i], four columns at a time
 #pragma unroll
     for (int h = 0; h < 8; h += 4) {
@@ -165,6 +182,7 @@ __device__ __forceinline__ V2 matvec(const double (&a)[8][8], const double (&dg)
             for (int j = 0; j < 4; ++j) s[j] = fma(a[i][h + j], xr[i], s[j]);
         if (L.has_blk) sts_f64x4(L.ct_w2 + h * 8, s[0], s[1], s[2], s[3]);
     }
+    MVT_AT(2);
     __syncwarp();
     double p[kSlots], q[kSlots];
 #pragma unroll
@@ -172,18 +190,37 @@ __device__ __forceinline__ V2 matvec(const double (&a)[8][8], const double (&dg)
     V2 y;
     y.a = ((p[0] + p[1]) + (p[2] + p[3])) + ((p[4] + p[5]) + (p[6] + d00));
     y.b = ((q[0] + q[1]) + (q[2] + q[3])) + ((q[4] + q[5]) + (q[6] + d10));
+    MVT_AT(3);
     return y;
 }
 
-struct State { V2 b, lo, hi, x0; double cs; };
+struct State {
+    V2 x0;
+    double cs;
+    uint32_t vcur;              // this lane's pair in Smem::vcur[0]
+    __device__ __forceinline__ V2 ld(uint32_t off) const { V2 r; lds_f64x2(vcur + off, r.a, r.b); return r; }
+    __device__ __forceinline__ V2 b() const { return ld(0); }
+    __device__ __forceinline__ V2 lo() const { return ld(kN * 8); }
+    __device__ __forceinline__ V2 hi() const { return ld(2 * kN * 8); }
+};
 
+#ifdef CCQP_BSYM_TIMING     // debug build: cycles of the pieces of a BBPGD iteration, returned in the result record
+#define BSYM_T(var) const long long var = clock64()
+#else
+#define BSYM_T(var)
+#endif
 template <int SOLVER, bool WREG>
 __device__ __forceinline__ void solve_one(const BatchedCtx& c, const double (&a)[8][8], const double (&dg)[2][8], const Lane& L,
                                           const State& s, const double* uni, V2& xsol, BatchedOut& o) {
     int mv = 0, gemv = 0, iters = 0, draws = 0, status = 0;
+#ifdef CCQP_BSYM_TIMING
+    long long tc_mv = 0, tc_sum = 0, tc_div = 0, tc_all = 0;
+    MvT mvt = {{0, 0, 0, 0, 0, 0}};
+    const long long tc_begin = clock64();
+#endif
     double res = NAN;
     const int maxmv = c.max_mv_i;
-    auto P = [&](V2 t) { return clamp2(t, s.lo, s.hi); };
+    auto P = [&](V2 t) { return clamp2(t, s.lo(), s.hi()); };
     auto MV = [&](V2 v) { gemv++; return matvec(a, dg, L, v); };
     auto resid2 = [&](V2 x, V2 g) { const V2 d = s.cs * (x - P(x - kGd * g)); return hs(d * d); };
 
@@ -191,7 +228,7 @@ __device__ __forceinline__ void solve_one(const BatchedCtx& c, const double (&a)
         // solvers.py:114-170, 606-669, 741-819 (batched.cuh solve_one, two unknowns per lane)
         V2 x = s.x0, xm = s.x0, g, gm, xmin = s.x0, gmin = s.x0;
         double resmin = INFINITY;
-        gm = MV(xm) + s.b; mv = 1;
+        gm = MV(xm) + s.b(); mv = 1;
         double r1[1] = {resid2(xm, gm)};
         wsum<1>(r1);
         double res2 = r1[0];
@@ -204,13 +241,25 @@ __device__ __forceinline__ void solve_one(const BatchedCtx& c, const double (&a)
                 step = q[0] / q[1];
             }
             for (;;) {
+                BSYM_T(t0);
                 x = P(xm - step * gm);
-                g = MV(x) + s.b; mv++;
+                BSYM_T(t1);
+#ifdef CCQP_BSYM_TIMING
+                gemv++; g = matvec(a, dg, L, x, &mvt) + s.b(); mv++;
+#else
+                g = MV(x) + s.b(); mv++;
+#endif
+                BSYM_T(t2);
                 if (mv >= maxmv) break;
                 const V2 sx = x - xm, sy = g - gm;
                 double q[3] = {resid2(x, g), hs(sx * sx), hs(sx * sy)};
+                BSYM_T(t3);
                 if (SOLVER == CCQP_SOLVER_PGD) { double q1[1] = {q[0]}; wsum<1>(q1); q[0] = q1[0]; }
                 else wsum<3>(q);
+                BSYM_T(t4);
+#ifdef CCQP_BSYM_TIMING
+                tc_mv += t2 - t1; tc_sum += t4 - t3; tc_div += (t1 - t0) ; tc_all += t3 - t2;
+#endif
                 res2 = q[0];
                 iters++;
                 if (res2 < c.thr_lt) break;
@@ -235,7 +284,7 @@ __device__ __forceinline__ void solve_one(const BatchedCtx& c, const double (&a)
         static_assert(SOLVER == CCQP_SOLVER_SPG, "solver");
         // solvers.py:906-975
         V2 x = s.x0;
-        V2 g = MV(x) + s.b;
+        V2 g = MV(x) + s.b();
         const V2 ag = MV(g);
         double q0[3] = {hs(g * x), hs(g * g), hs(g * ag)};
         wsum<3>(q0);
@@ -279,6 +328,18 @@ __device__ __forceinline__ void solve_one(const BatchedCtx& c, const double (&a)
     o.mv = mv; o.gemv = gemv; o.iters = iters; o.draws = draws;
     o.converged = (mv < maxmv && status == 0) ? 1 : 0;
     o.status = status;
+#ifdef CCQP_BSYM_TIMING
+    {   // residual <- cycles of the whole solve; gemv <- per-iteration mat-vec; iters <- reduction; draws <- products; (projection in mv)
+        const int it = iters > 0 ? iters : 1;
+        o.residual = (double)(clock64() - tc_begin);
+        if (SOLVER == CCQP_SOLVER_BBPGD) {      // cumulative cycles inside the mat-vec, packed: after diag | after s1 | after s2 | end (12 bits each, /4)
+            long long pk = 0;
+            for (int k = 0; k < 4; ++k) pk |= ((mvt.t[k] / it / 4) & 0xfff) << (12 * k);
+            o.residual = (double)pk;
+        }
+        o.gemv = (int)(tc_mv / it); o.iters = (int)(tc_sum / it); o.draws = (int)(tc_all / it); o.mv = (int)(tc_div / it) + 1000000 * iters;
+    }
+#endif
 }
 
 template <int SOLVER, bool WREG>
@@ -373,14 +434,20 @@ __global__ void __launch_bounds__(32, kCtas) batched_sym_kernel(const BatchedCtx
                 for (int j = 0; j < 8; ++j)
                     dg[t][j] = (u0 + t < n && 8 * k + j < n) ? ldg_stream(Ap + (size_t)(u0 + t) * n + 8 * k + j) : 0.0;
         }
-        if (vstaged) {
-            s.b = {L.act0 ? sm.vstage[0][u0] : 0.0, L.act1 ? sm.vstage[0][u0 + 1] : 0.0};
-            s.lo = {L.act0 ? sm.vstage[1][u0] : 0.0, L.act1 ? sm.vstage[1][u0 + 1] : 0.0};
-            s.hi = {L.act0 ? sm.vstage[2][u0] : 0.0, L.act1 ? sm.vstage[2][u0 + 1] : 0.0};
-        } else {
-            s.b = {L.act0 ? c.b[vo] : 0.0, L.act1 ? c.b[vo + 1] : 0.0};
-            s.lo = {L.act0 ? c.lb[bo] : 0.0, L.act1 ? c.lb[bo + 1] : 0.0};
-            s.hi = {L.act0 ? c.ub[bo] : 0.0, L.act1 ? c.ub[bo + 1] : 0.0};
+        {
+            V2 vb, vl, vh;
+            if (vstaged) {
+                vb = {sm.vstage[0][u0], sm.vstage[0][u0 + 1]}; vl = {sm.vstage[1][u0], sm.vstage[1][u0 + 1]};
+                vh = {sm.vstage[2][u0], sm.vstage[2][u0 + 1]};
+            } else {
+                vb = {L.act0 ? c.b[vo] : 0.0, L.act1 ? c.b[vo + 1] : 0.0};
+                vl = {L.act0 ? c.lb[bo] : 0.0, L.act1 ? c.lb[bo + 1] : 0.0};
+                vh = {L.act0 ? c.ub[bo] : 0.0, L.act1 ? c.ub[bo + 1] : 0.0};
+            }
+            s.vcur = smem_u32(&sm.vcur[0][u0]);     // read back by this lane only: no synchronisation needed
+            sts_f64x2(s.vcur, L.act0 ? vb.a : 0.0, L.act1 ? vb.b : 0.0);
+            sts_f64x2(s.vcur + kN * 8, L.act0 ? vl.a : 0.0, L.act1 ? vl.b : 0.0);
+            sts_f64x2(s.vcur + 2 * kN * 8, L.act0 ? vh.a : 0.0, L.act1 ? vh.b : 0.0);
         }
         s.x0 = {(L.act0 && c.x0) ? c.x0[vo] : 0.0, (L.act1 && c.x0) ? c.x0[vo + 1] : 0.0};
         s.cs = 1.0 / (3 * (double)n * kGd);

@@ -868,6 +868,7 @@ ccqp_status ccqp_microbench(ccqp_handle* h, double* cycles_per_op, int32_t n_out
         h->launches += 1;
     }
     for (int k = 0; k < PROBE_COUNT; ++k) cycles_per_op[k] = (double)cyc[k] / reps;
+    cycles_per_op[PROBE_DFMA_X8_REUSE] /= 8; cycles_per_op[PROBE_DFMA_X8_2RF] /= 8; cycles_per_op[PROBE_DFMA_MATVEC64] /= 64;   // per DFMA
     return CCQP_OK;
 }
 

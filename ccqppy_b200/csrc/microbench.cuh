@@ -33,7 +33,7 @@ constexpr int kPeakFmaPerIter = 64;         // per thread per loop trip
 enum ProbeKind : int {
     PROBE_DFMA = 0, PROBE_DADD, PROBE_DMUL, PROBE_SHFL_DADD, PROBE_DIV, PROBE_SQRT, PROBE_LDS128_BCAST, PROBE_LDS128_DISTINCT,
     PROBE_STS_BAR_LDS, PROBE_BAR, PROBE_DSETP_SEL, PROBE_DMMA, PROBE_DMMA_X8, PROBE_WARPSUM_DMMA, PROBE_WARPSUM_SHFL,
-    PROBE_DMMA_X8_DFMA_X8, PROBE_COUNT
+    PROBE_DMMA_X8_DFMA_X8, PROBE_DFMA_X8_REUSE, PROBE_DFMA_X8_2RF, PROBE_DFMA_MATVEC64, PROBE_COUNT
 };
 
 // D(8x8) = A(8x4) B(4x8) + C on the FP64 tensor path (SASS DMMA.884): lane l holds A[l/4][l%4], B[l%4][l/4],
@@ -119,6 +119,36 @@ _Pragma("unroll")
         })
 #pragma unroll
         for (int u = 0; u < 8; ++u) keep += f[u];
+    }
+    // Issue rate of INDEPENDENT DFMAs as a function of where the operands come from (one warp per SM sub-partition):
+    //   x8_reuse  : f[u] = fma(f[u], w, w)         one fresh register operand per instruction (fp64_peak_kernel's pattern)
+    //   x8_2rf    : f[u] = fma(g[u], w, f[u])      two (multiplicand and accumulator), 8 + 8 registers
+    //   matvec64  : s[i] = fma(a[i][j], x[j], s[i]) the register-resident 8 x 8 block of the batched kernels: two fresh operands, the
+    //               multiplicand never repeats within a trip (64 registers)
+    {
+        double f[8], g8[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { f[u] = v * 1e-3 + u; g8[u] = w + 1e-3 * u; }
+        PROBE(PROBE_DFMA_X8_REUSE, {
+_Pragma("unroll")
+            for (int u = 0; u < 8; ++u) f[u] = fma(f[u], w, w); })
+        PROBE(PROBE_DFMA_X8_2RF, {
+_Pragma("unroll")
+            for (int u = 0; u < 8; ++u) f[u] = fma(g8[u], w, f[u]); })
+        double a[8][8], xx[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            xx[i] = 1e-6 * (w + i);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[i][j] = 1e-3 * (x + i) + 1e-6 * (t + j);
+        }
+        PROBE(PROBE_DFMA_MATVEC64, {
+_Pragma("unroll")
+            for (int j = 0; j < 8; ++j)
+_Pragma("unroll")
+                for (int i = 0; i < 8; ++i) f[i] = fma(a[i][j], xx[j], f[i]); })
+#pragma unroll
+        for (int u = 0; u < 8; ++u) keep += f[u] + g8[u];
     }
     v += keep;
 #undef PROBE

@@ -329,6 +329,7 @@ class CCQPSolverBase(ABC):
         self._solution_converged = rec["conv"].astype(bool)
         self._solution_num_matrix_vector_mults = rec["mv"].copy()
         self._batched_status = rec["status"].copy()
+        self._batched_records = rec.copy()          # every field of the per-problem ccqp_result (tools/)
         self._gpu_time = float(summary.gpu_seconds)
         self._hbm_bytes = float(summary.hbm_bytes)
         self._gemv_count = int(summary.gemv_count)

@@ -241,8 +241,10 @@ ccqp_status ccqp_fp64_peak(ccqp_handle* h, int blocks_per_sm, int threads_per_bl
 /* SM cycles per dependent operation, one warp, in the order DFMA, DADD, DMUL, SHFL.64+DADD, IEEE
  * division+DADD, sqrt+DADD, LDS.128 (all lanes one address)+DADD, LDS.128 (distinct)+DADD,
  * STS+bar+LDS+DADD+bar, bar.sync (64 threads), DSETP+select+DADD, then the FP64 tensor path (DMMA.884 dependent,
- * 8 independent, a 32-lane sum as DMMA+DADD+DMMA against 5 shuffle stages, DMMA mixed with DFMA).  n_out >= 16.  Feeds the cycle
- * model of the batched kernel in DESIGN.md. */
+ * 8 independent, a 32-lane sum as DMMA+DADD+DMMA against 5 shuffle stages, DMMA mixed with DFMA), then the issue interval of
+ * INDEPENDENT DFMAs per instruction: 8 chains with one fresh register operand, with two, and the 8 x 8 register-block mat-vec of
+ * the batched kernels (two fresh operands, 64 distinct multiplicands).  n_out >= 19.  Feeds the cycle model of the batched
+ * kernel in DESIGN.md. */
 ccqp_status ccqp_microbench(ccqp_handle* h, double* cycles_per_op, int32_t n_out);
 
 /* ---- multi-GPU (row-sharded dense solves, one process per GPU) --------------------------------
