@@ -24,7 +24,8 @@ EXPORTS = ["ccqp_abi_version", "ccqp_status_string", "ccqp_last_error", "ccqp_cr
            "ccqp_set_stream", "ccqp_get_info", "ccqp_set_matrix", "ccqp_set_matrix_csr", "ccqp_set_projection", "ccqp_solve", "ccqp_solve_async", "ccqp_solve_wait",
            "ccqp_solve_batched", "ccqp_gemv", "ccqp_gemv_timed", "ccqp_project", "ccqp_normal", "ccqp_comm_export",
            "ccqp_comm_attach", "ccqp_comm_prepare", "ccqp_comm_detach", "ccqp_debug_divide", "ccqp_fp64_peak",
-           "ccqp_microbench", "ccqp_debug_emulate_ranks", "ccqp_debug_solve_emulated", "ccqp_projected_gradient", "ccqp_solve_batched_table", "ccqp_solve_batched_sym"]
+           "ccqp_microbench", "ccqp_debug_emulate_ranks", "ccqp_debug_solve_emulated", "ccqp_projected_gradient", "ccqp_solve_batched_table", "ccqp_solve_batched_sym",
+           "ccqp_get_upload_info", "ccqp_set_matrix_symmetric", "ccqp_host_matrix_is_block_symmetric", "ccqp_upload_block_rows"]
 
 
 class Block(C.Structure):
@@ -84,6 +85,12 @@ def load():
     lib.ccqp_solve_batched_sym.argtypes = lib.ccqp_solve_batched.argtypes
     lib.ccqp_solve_batched_table.argtypes = [vp, i32, C.POINTER(Params), i64, i64, dp, dp, dp, C.POINTER(Block), i64, dp, i64, dp, i64,
                                              dp, i32, C.POINTER(Result), C.POINTER(Result)]
+    lib.ccqp_set_matrix_symmetric.argtypes = [vp, dp, i64, i64, i32]
+    lib.ccqp_get_upload_info.argtypes = [vp, C.POINTER(i64), C.POINTER(i32)]
+    lib.ccqp_host_matrix_is_block_symmetric.argtypes = [dp, i64, i64, i32]
+    lib.ccqp_host_matrix_is_block_symmetric.restype = i32
+    lib.ccqp_upload_block_rows.argtypes = []
+    lib.ccqp_upload_block_rows.restype = i32
     lib.ccqp_gemv.argtypes = [vp, dp, dp, i32]
     lib.ccqp_gemv_timed.argtypes = [vp, dp, dp, i32, C.POINTER(C.c_double)]
     lib.ccqp_project.argtypes = [vp, dp, dp, i32]
@@ -158,6 +165,12 @@ class Handle:
         out = (C.c_double * len(self.PROBES))()
         check(self.h, self.lib.ccqp_microbench(self.h, out, len(self.PROBES)))
         return dict(zip(self.PROBES, [float(v) for v in out]))
+
+    def upload_info(self):
+        """(bytes, mirrored) of the last host -> device matrix copy (ccqp_get_upload_info)."""
+        nbytes, mirrored = C.c_int64(), C.c_int32()
+        check(self.h, self.lib.ccqp_get_upload_info(self.h, C.byref(nbytes), C.byref(mirrored)))
+        return nbytes.value, bool(mirrored.value)
 
     def info(self):
         sm, grid, thr, smem = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int64()

@@ -52,6 +52,8 @@ struct ccqp_handle {
     DevBuf ptr_own, idx_own, val_own, tile_row;   // tile_row: see csr_tile_rows_kernel
     long long nnz = 0;
     bool have_matrix() const { return dA != nullptr || d_val != nullptr; }
+    bool upload_mirrored = false;       // the last host matrix was symmetric and crossed PCIe as its upper block triangle
+    long long upload_bytes = 0;         // bytes of the last host -> device matrix copy
     long long n = 0, lda = 0, row0 = 0, nrows = 0;
     // projection
     bool have_proj = false;
@@ -403,8 +405,8 @@ ccqp_status ccqp_get_info(const ccqp_handle* h, int32_t* sm_count, int32_t* dens
     return CCQP_OK;
 }
 
-ccqp_status ccqp_set_matrix(ccqp_handle* h, const double* A, int64_t n, int64_t lda, int64_t row_begin, int64_t n_rows,
-                            int memtype) {
+static ccqp_status set_matrix_dense(ccqp_handle* h, const double* A, int64_t n, int64_t lda, int64_t row_begin, int64_t n_rows,
+                                    int memtype, bool declared_symmetric) {
     if (!h || !A || n <= 0 || n >= (1LL << 31) - 256 || lda < n || row_begin < 0 || n_rows <= 0 || row_begin + n_rows > n)
         return CCQP_ERR_INVALID_ARG;
     CU(h, cudaSetDevice(h->device));
@@ -415,12 +417,40 @@ ccqp_status ccqp_set_matrix(ccqp_handle* h, const double* A, int64_t n, int64_t 
     } else {
         const long long ldd = round_up(n, 4);   // keep rows 32-byte aligned for the 256-bit loads
         CU(h, h->a_own.ensure((size_t)n_rows * ldd * 8 + 64));
-        CU(h, cudaMemcpy2DAsync(h->a_own.p, (size_t)ldd * 8, A, (size_t)lda * 8, (size_t)n * 8, (size_t)n_rows,
-                                cudaMemcpyHostToDevice, h->stream));
+        if (row_begin == 0 && n_rows == n) {    // a whole matrix: half of the PCIe traffic if it turns out to be symmetric (upload.cu)
+            CU(h, upload_square_matrix(h->stream, h->a_own.as<double>(), ldd, A, n, lda, declared_symmetric, &h->upload_mirrored, &h->upload_bytes));
+        } else {
+            CU(h, cudaMemcpy2DAsync(h->a_own.p, (size_t)ldd * 8, A, (size_t)lda * 8, (size_t)n * 8, (size_t)n_rows,
+                                    cudaMemcpyHostToDevice, h->stream));
+            h->upload_mirrored = false; h->upload_bytes = n_rows * n * 8;
+        }
         h->dA = h->a_own.as<double>(); h->lda = ldd;
     }
     return CCQP_OK;
 }
+
+ccqp_status ccqp_set_matrix(ccqp_handle* h, const double* A, int64_t n, int64_t lda, int64_t row_begin, int64_t n_rows,
+                            int memtype) {
+    return set_matrix_dense(h, A, n, lda, row_begin, n_rows, memtype, false);
+}
+
+ccqp_status ccqp_set_matrix_symmetric(ccqp_handle* h, const double* A, int64_t n, int64_t lda, int memtype) {
+    return set_matrix_dense(h, A, n, lda, 0, n, memtype, true);
+}
+
+ccqp_status ccqp_get_upload_info(ccqp_handle* h, int64_t* bytes, int32_t* mirrored) {
+    if (!h) return CCQP_ERR_INVALID_ARG;
+    if (bytes) *bytes = h->upload_bytes;
+    if (mirrored) *mirrored = h->upload_mirrored ? 1 : 0;
+    return CCQP_OK;
+}
+
+int32_t ccqp_host_matrix_is_block_symmetric(const double* A, int64_t n, int64_t lda, int32_t threads) {
+    if (!A || n <= 0 || lda < n) return -1;
+    return host_matrix_mirrors(A, n, lda, threads) ? 1 : 0;
+}
+
+int32_t ccqp_upload_block_rows(void) { return upload_block_rows(); }
 
 ccqp_status ccqp_set_matrix_csr(ccqp_handle* h, const int64_t* indptr, const int32_t* indices, const double* values,
                                 int64_t n, int64_t nnz, int64_t row_begin, int64_t n_rows, int memtype) {

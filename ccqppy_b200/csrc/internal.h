@@ -27,6 +27,13 @@ int batched_solve_table_entry(cudaStream_t stream, int sm_count, int solver, con
                               int memtype, ccqp_result* results, ccqp_result* summary, cudaEvent_t ev0, cudaEvent_t ev1, int* launches,
                               std::string& err, const std::function<void*(size_t)>& alloc);
 
+// upload.cu -- host -> device copy of a square matrix; a symmetric one crosses PCIe as its upper block triangle (checked on the host
+// while the copies run) and is mirrored on the device: the device copy is bit-identical to a full upload either way
+cudaError_t upload_square_matrix(cudaStream_t stream, double* dst, long long ldd, const double* A, long long n, long long lda,
+                                 bool declared_symmetric, bool* used_mirror, long long* bytes);
+bool host_matrix_mirrors(const double* A, long long n, long long lda, int threads);
+int upload_block_rows();
+
 // emu.cu -- one cooperative launch of dense_kernel_emu<solver> over world * G CTAs
 cudaError_t launch_dense_emu(int solver, const DenseCtx* d_ctxs, int world, int G, size_t smem, cudaStream_t stream);
 

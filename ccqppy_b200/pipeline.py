@@ -83,9 +83,10 @@ class SolvePipeline:
         self._done[slot.ticket] = r
         slot.keep = slot.xout = slot.ticket = None
 
-    def submit(self, A, b, x0=None, convex_proj_op=None, uniforms=None):
-        """Enqueue one solve; returns its ticket (0, 1, 2, ...).  Blocks only if the slot it lands on still
-        has a solve in flight (then that one is collected first)."""
+    def submit(self, A, b, x0=None, convex_proj_op=None, uniforms=None, symmetric=False):
+        """Enqueue one solve; returns its ticket (0, 1, 2, ...).  Blocks if the slot it lands on still has a solve in
+        flight (that one is collected first) and for the host-side symmetry test of a large A (`solve()`'s docstring);
+        `symmetric=True` declares the symmetry and skips the test."""
         s = self.solver
         n = int(b.shape[0])
         if convex_proj_op is None:
@@ -108,7 +109,10 @@ class SolvePipeline:
         _capi.check(h.h, lib.ccqp_set_projection(h.h, blocks.ptr, len(blocks), ctypes.c_void_p(par.ctypes.data), params.size))
         pa, mem, _ = _capi.f64_ptr(A64)
         lda = A64.stride(0) if _is_torch(A64) else n
-        _capi.check(h.h, lib.ccqp_set_matrix(h.h, pa, n, lda, 0, n, mem))      # asynchronous from pinned memory
+        if symmetric:
+            _capi.check(h.h, lib.ccqp_set_matrix_symmetric(h.h, pa, n, lda, mem))
+        else:
+            _capi.check(h.h, lib.ccqp_set_matrix(h.h, pa, n, lda, 0, n, mem))  # the copies are asynchronous from pinned memory
         xout = self._pinned(n)
         ptr = lambda v: None if v is None else _capi.f64_ptr(v)[0]
         prm = s._params()

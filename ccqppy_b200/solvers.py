@@ -141,12 +141,17 @@ class CCQPSolverBase(ABC):
         if used:
             np.random.random_sample(int(used))
 
-    def solve(self, A, b, x0=None, convex_proj_op=None, *, uniforms=None, device=-1):
+    def solve(self, A, b, x0=None, convex_proj_op=None, *, uniforms=None, device=-1, symmetric=False):
         """min 1/2 x^T A x + b^T x  s.t. x in Omega   (the gradient is A x + b, solvers.py:133).
 
         A : (n, n) dense array / tensor; b : (n,); x0 : (n,) or None (zeros);
         convex_proj_op : an operator of `ccqppy_b200.solution_spaces` (default Identity).
-        Returns self; results are the `solution*` properties, as in the reference."""
+        Returns self; results are the `solution*` properties, as in the reference.
+
+        A host-resident dense A that is symmetric crosses PCIe as its upper block triangle only (found out by a host-side
+        test that runs while the copy engine works; the device copy is bit-identical to a full upload, and any other A is
+        uploaded whole -- `ccqp_set_matrix`).  `symmetric=True` (extension) declares the symmetry instead: no test, the
+        blocks below the block diagonal of A are never read (`ccqp_set_matrix_symmetric`)."""
         num_unknowns = b.shape[0]
         if convex_proj_op is None:
             convex_proj_op = ss.IdentityProjOp(num_unknowns)
@@ -182,7 +187,10 @@ class CCQPSolverBase(ABC):
         else:
             pa, mem_a, _ka = _capi.f64_ptr(A64)
             lda = A64.stride(0) if _is_torch(A64) else num_unknowns
-            _capi.check(h.h, lib.ccqp_set_matrix(h.h, pa, num_unknowns, lda, 0, num_unknowns, mem_a))
+            if symmetric:
+                _capi.check(h.h, lib.ccqp_set_matrix_symmetric(h.h, pa, num_unknowns, lda, mem_a))
+            else:
+                _capi.check(h.h, lib.ccqp_set_matrix(h.h, pa, num_unknowns, lda, 0, num_unknowns, mem_a))
         blocks, params, _rows = convex_proj_op.descriptor()
         pp, _, _kp = _capi.f64_ptr(params if params.size else np.zeros(1))
         _capi.check(h.h, lib.ccqp_set_projection(h.h, blocks.ptr, len(blocks), pp, params.size))

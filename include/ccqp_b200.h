@@ -138,6 +138,26 @@ ccqp_status ccqp_get_info(const ccqp_handle* h, int32_t* sm_count, int32_t* dens
 ccqp_status ccqp_set_matrix(ccqp_handle* h, const double* A, int64_t n, int64_t lda,
                             int64_t row_begin, int64_t n_rows, int memtype);
 
+/* What the last ccqp_set_matrix() from HOST memory moved.  A whole matrix (row_begin = 0, n_rows = n, n >= 2048) that is
+ * symmetric crosses PCIe as its upper block triangle only (row blocks of ccqp_upload_block_rows() rows, each from its first
+ * column on): the copies are enqueued first, host threads then compare A[i][j] with A[j][i] for every entry below the block
+ * diagonal while the copy engine works, and a device kernel mirrors the uploaded part -- the device copy is bit-identical to
+ * a full upload.  (The test runs only where the process has at least 12 hardware threads: it reads all of A.)  A matrix that is not symmetric (or holds a NaN, or a -0.0 / +0.0 pair) gets its remaining blocks uploaded
+ * after all.  The reference takes any square A (solvers.py:94, A.dot(v) at :133); the solver sees exactly that matrix
+ * either way.  CCQP_SYM_UPLOAD=0 in the environment turns the scheme off. */
+ccqp_status ccqp_get_upload_info(ccqp_handle* h, int64_t* bytes, int32_t* mirrored);
+/* ccqp_set_matrix() for a whole matrix the CALLER declares symmetric (the dsymv('U') contract at the granularity of
+ * ccqp_upload_block_rows() rows): from host memory only the upper block triangle is read and uploaded, no test is made, and
+ * the solver works on that triangle mirrored -- which is A itself when the declaration is true.  Device memory: the same as
+ * ccqp_set_matrix (A is used in place, both triangles are read).  Saves the host-side test, which reads all of A and competes
+ * with the copy engine for host memory bandwidth (n = 32768: a stream of solves at ~80 ms per solve instead of ~140). */
+ccqp_status ccqp_set_matrix_symmetric(ccqp_handle* h, const double* A, int64_t n, int64_t lda, int memtype);
+/* The host-side test of that scheme (pure host code, usable without a GPU): 1 if every entry below the block diagonal
+ * equals its mirror image bit for bit and is not a NaN, 0 if not, -1 for invalid arguments.  threads <= 0: all the
+ * process may run on. */
+int32_t ccqp_host_matrix_is_block_symmetric(const double* A, int64_t n, int64_t lda, int32_t threads);
+int32_t ccqp_upload_block_rows(void);
+
 /* Operator-form Hessian in CSR.  The reference accepts any `A` with a .dot (solvers.py:133), in particular
  * scipy.sparse matrices (contact-style Hessians D^T M^-1 D are sparse); this is that case.  indptr has
  * n_rows + 1 entries RELATIVE to the shard (indptr[0] = 0, indptr[n_rows] = nnz), indices are column ids
