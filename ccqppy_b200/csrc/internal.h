@@ -31,6 +31,7 @@ int batched_solve_table_entry(cudaStream_t stream, int sm_count, int solver, con
 // while the copies run) and is mirrored on the device: the device copy is bit-identical to a full upload either way
 cudaError_t upload_square_matrix(cudaStream_t stream, double* dst, long long ldd, const double* A, long long n, long long lda,
                                  bool declared_symmetric, bool* used_mirror, long long* bytes);
+cudaError_t mirror_lower(cudaStream_t stream, double* dst, long long n, long long ldd);
 bool host_matrix_mirrors(const double* A, long long n, long long lda, int threads);
 int upload_block_rows();
 

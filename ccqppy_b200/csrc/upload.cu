@@ -8,7 +8,9 @@
 //   2. meanwhile host threads compare A[i][j] with A[j][i] for every pair the mirror step would fill in, tile by tile (two
 //      32 KB tiles per step, both cache resident), stopping at the first difference (NaNs count as different);
 //   3. symmetric: one kernel mirrors the uploaded part into the blocks below the diagonal -- the device copy is then
-//      BIT-IDENTICAL to a full upload; not symmetric: the missing blocks are uploaded after all (the full copy, in two parts).
+//      BIT-IDENTICAL to a full upload.  (The kernel is launched by the first user of the matrix, AFTER that user's own small
+//      host -> device copies: a kernel between two groups of copies of one stream kept the solver kernel behind the copies
+//      another stream enqueued later -- a stream of solves lost the overlap of upload k+1 with solve k; tools/e2e_timeline.py); not symmetric: the missing blocks are uploaded after all (the full copy, in two parts).
 // Either way the solver sees exactly the matrix the caller passed.  CCQP_SYM_UPLOAD=0 turns the scheme off.
 #include <algorithm>
 #include <atomic>
@@ -54,6 +56,12 @@ __global__ void __launch_bounds__(256) mirror_lower_kernel(double* __restrict__ 
 // diagonal of A are never read.  *used_mirror reports which way it went, *bytes what crossed PCIe.  Returns the first CUDA error.
 int upload_block_rows() { return kUpBlock; }
 
+cudaError_t mirror_lower(cudaStream_t stream, double* dst, long long n, long long ldd) {
+    const unsigned tiles = (unsigned)((n + kMirTile - 1) / kMirTile);
+    mirror_lower_kernel<<<dim3(tiles, tiles), 256, 0, stream>>>(dst, n, ldd);
+    return cudaGetLastError();
+}
+
 bool host_matrix_mirrors(const double* A, long long n, long long lda, int threads) {
     return host_lower_blocks_mirror_upper(A, n, lda, kUpBlock, threads > 0 ? threads : host_threads_available());
 }
@@ -78,9 +86,7 @@ cudaError_t upload_square_matrix(cudaStream_t stream, double* dst, long long ldd
         if (e != cudaSuccess) return e;
     }
     if (declared_symmetric || host_lower_blocks_mirror_upper(A, n, lda, kUpBlock, threads)) {  // 2. (runs while the copies are in flight)
-        const unsigned tiles = (unsigned)((n + kMirTile - 1) / kMirTile);
-        mirror_lower_kernel<<<dim3(tiles, tiles), 256, 0, stream>>>(dst, n, ldd);   // 3a.
-        *used_mirror = true;
+        *used_mirror = true;                                                        // 3a. mirror_lower(), launched by the caller
         *bytes = 0;
         for (long long i0 = 0; i0 < n; i0 += kUpBlock) *bytes += std::min<long long>(kUpBlock, n - i0) * (n - i0) * 8;
         return cudaGetLastError();

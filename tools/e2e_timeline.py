@@ -40,18 +40,40 @@ class Timed:
         return wrapped
 
 
-names = ("ccqp_set_matrix", "ccqp_set_projection", "ccqp_solve_async", "ccqp_solve_wait")
+# raw upload rates first: the copy alone, nothing else on the GPU
+import ctypes
+h = _capi.Handle(0)
+pa, mem, _ = _capi.f64_ptr(A_host)
+for label, call in (("full (CCQP_SYM_UPLOAD=0)", "full"), ("upper block triangle, declared", "decl"), ("upper block triangle + host test", "auto")):
+    for rep in range(2):
+        os.environ["CCQP_SYM_UPLOAD"] = "0" if call == "full" else "1"
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        if call == "decl":
+            _capi.check(h.h, lib.ccqp_set_matrix_symmetric(h.h, pa, n, n, mem))
+        else:
+            _capi.check(h.h, lib.ccqp_set_matrix(h.h, pa, n, n, 0, n, mem))
+        t_call = time.perf_counter() - t
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t
+    nb = h.upload_info()[0]
+    print("upload alone: %-36s call returns after %6.1f ms, done after %6.1f ms, %.2f GB -> %.1f GB/s" % (label, 1e3 * t_call, 1e3 * dt, nb / 1e9, nb / dt / 1e9))
+os.environ["CCQP_SYM_UPLOAD"] = "1"
+h.close()
+mode = sys.argv[2] if len(sys.argv) > 2 else "auto"
+sym = mode == "declared"
+names = ("ccqp_set_matrix", "ccqp_set_matrix_symmetric", "ccqp_set_projection", "ccqp_solve_async", "ccqp_solve_wait")
 pipe = SolvePipeline(solvers.CCQPSolverSPG(bench.TOL, bench.MAX_MV), depth=2, device=0)
 for s in pipe.slots:
     s.handle.lib = Timed(lib, names)
 for _ in range(2):
-    pipe.submit(A_host, b_host, convex_proj_op=op, uniforms=uni)
+    pipe.submit(A_host, b_host, convex_proj_op=op, uniforms=uni, symmetric=sym)
 pipe.results()
 torch.cuda.synchronize()
 log.clear()
 T0 = time.perf_counter()
 for _ in range(5):
-    pipe.submit(A_host, b_host, convex_proj_op=op, uniforms=uni)
+    pipe.submit(A_host, b_host, convex_proj_op=op, uniforms=uni, symmetric=sym)
 res = pipe.results()
 total = time.perf_counter() - T0
 for name, at, dur in log:
