@@ -20,7 +20,17 @@
 //     the only synchronisation, the dot products are pure shuffle butterflies (no shared-memory exchange, no CTA barrier).
 //   * 20 KB (the upper block triangle, compact) of the NEXT problem's A and its b / lb / ub rows land in shared memory by TMA row
 //     copies on one mbarrier while the current problem iterates; HBM traffic per problem drops from 32 KB to 18 KB.
-// Launch shape: 32 threads per CTA, 8 CTAs per SM (<= 255 registers, 27 KB of shared memory each).
+// Launch shape: 32 threads per CTA, 8 CTAs per SM (<= 255 registers, 28 KB of shared memory each; b / lb / ub of the current
+// problem live in shared memory: with them in registers ptxas split the row sums into two-chain groups).
+//
+// Measured (65 536 problems of n = 64, tol 1e-8, profiles/README.md): SPG 13.8 M QP/s against 12.9 M for batched.cuh (+7 %),
+// BBPGD 51.8 M against 61.0 M (-15 %).  Eight problems are in flight instead of six, but one problem's iteration is a longer
+// chain here: the mat-vec of a lone warp takes 930 cycles (x slices + diagonal rows 124, s1 308, s2 304, slots read + added
+// 196; CCQP_BSYM_TIMING build, tools/bsym_timing.py) against ~480 for the two warps of batched.cuh, because 144 DFMAs per lane
+// issue from ONE warp (2.9 cycles each out of a 64-entry register block: ccqp_microbench) where the full layout spreads 128
+// over two sub-partitions.  The DFMA count per problem is the same in both layouts, so is their operand traffic; what the
+// symmetric layout buys is register space (and half of the HBM reads), what it costs is the exchange through shared memory.
+// Hence: an opt-in for callers whose solver is SPG (or whose batch is HBM- or capacity-bound), not the default.
 #define CCQP_BATCHED_DEVICE_ONLY
 #include "batched.cuh"
 #include "internal.h"

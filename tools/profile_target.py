@@ -2,7 +2,7 @@
 
   part 1: three launches of the mat-vec hook kernel at n=32768 (the hot phase in isolation)
   part 2: one whole SPG solve at n=16384 (A = 2.1 GB >> L2), the persistent solver kernel
-  part 3: batched BBPGD and SPG, 16384 problems of n=64
+  part 3: batched BBPGD and SPG, 16384 problems of n=64 (`batched_sym`: through ccqp_solve_batched_sym)
 """
 import ctypes as C
 import os
@@ -38,14 +38,15 @@ if "spg" in which:
     s.solve(A, b, convex_proj_op=ss.BoxProjOp(n), uniforms=uni)
     print("spg n=%d: mv %d, %.2f ms, %.0f GB/s" % (n, s.solution_gemv_count, 1e3 * s.solution_gpu_time, s.solution_hbm_bytes / s.solution_gpu_time / 1e9))
     del A
-if "batched" in which:
+if "batched" in which or "batched_sym" in which:
     B, nb = 16384, 64
     G = torch.randn((B, nb, nb), generator=g, device=dev, dtype=torch.float64)
     A = G @ G.transpose(1, 2) / nb + torch.eye(nb, device=dev, dtype=torch.float64)
+    A = 0.5 * (A + A.transpose(1, 2))
     b = -(A @ (1 - 4 * torch.rand((B, nb, 1), generator=g, device=dev, dtype=torch.float64))).squeeze(-1)
     lb, ub = -torch.ones_like(b), torch.ones_like(b)
     uni = torch.rand((B, 256), generator=g, device=dev, dtype=torch.float64)
     for cls in (solvers.CCQPSolverBBPGD, solvers.CCQPSolverSPG):
         s = cls(1e-8, 5000); s.quiet = True
-        s.solve_batched(A, b, lb, ub, uniforms=uni)
+        s.solve_batched(A, b, lb, ub, uniforms=uni, symmetric="batched_sym" in which)
         print("batched %s: %.3f ms, %.1f M QP/s" % (s.name, 1e3 * s.solution_gpu_time, B / s.solution_gpu_time / 1e6))
