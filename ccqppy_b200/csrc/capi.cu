@@ -427,6 +427,7 @@ static ccqp_status set_matrix_dense(ccqp_handle* h, const double* A, int64_t n, 
     h->mirror_pending = false;
     if (memtype == CCQP_MEM_DEVICE) {
         h->dA = A; h->lda = lda;
+        h->upload_mirrored = false; h->upload_bytes = 0;
     } else {
         const long long ldd = round_up(n, 4);   // keep rows 32-byte aligned for the 256-bit loads
         CU(h, h->a_own.ensure((size_t)n_rows * ldd * 8 + 64));
@@ -474,6 +475,7 @@ ccqp_status ccqp_set_matrix_csr(ccqp_handle* h, const int64_t* indptr, const int
     CU(h, cudaSetDevice(h->device));
     h->n = n; h->row0 = row_begin; h->nrows = n_rows; h->nnz = nnz;
     h->dA = nullptr; h->lda = 0;
+    h->mirror_pending = false; h->upload_mirrored = false; h->upload_bytes = 0;
     if (memtype == CCQP_MEM_DEVICE) {
         h->d_ptr = reinterpret_cast<const long long*>(indptr); h->d_idx = indices; h->d_val = values;
     } else {

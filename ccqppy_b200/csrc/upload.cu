@@ -75,8 +75,10 @@ cudaError_t upload_square_matrix(cudaStream_t stream, double* dst, long long ldd
     // cores (and with them the memory bandwidth) to do that faster than PCIe moves the other half -- measured on a 16-thread
     // host: 70 ms alone / ~95 ms next to the copies against 156 ms for the full upload at n = 32768.
     const int threads = host_threads_available();
-    const bool enabled = declared_symmetric || (!(env && atoi(env) == 0) && threads >= 12);
-    if (!enabled || n < 2 * kUpBlock)
+    // a declared symmetry holds at every size (the blocks below the block diagonal are never read); the test only pays off for
+    // matrices of at least two blocks by two
+    const bool enabled = declared_symmetric ? n > kUpBlock : (!(env && atoi(env) == 0) && threads >= 12 && n >= 2 * kUpBlock);
+    if (!enabled)
         return cudaMemcpy2DAsync(dst, (size_t)ldd * 8, A, (size_t)lda * 8, (size_t)n * 8, (size_t)n, cudaMemcpyHostToDevice, stream);
     cudaError_t e;
     for (long long i0 = 0; i0 < n; i0 += kUpBlock) {         // 1. upper block triangle

@@ -87,12 +87,12 @@ def test_gemv_after_each_upload_path():
     assert torch.cuda.is_available()
 
 
-def test_declared_symmetric_reads_upper_block_triangle_only():
+@pytest.mark.parametrize("n", [2600, 1500])
+def test_declared_symmetric_reads_upper_block_triangle_only(n):
     """solve(..., symmetric=True) -> ccqp_set_matrix_symmetric: no test, the blocks below the block diagonal of the host
     matrix are never read (NaN-poisoned they change nothing) and the result is bit-identical to the plain solve of the
     symmetric matrix; SolvePipeline.submit(symmetric=True) goes the same way."""
     from ccqppy_b200.pipeline import SolvePipeline
-    n = 2600
     B = _capi.load().ccqp_upload_block_rows()
     A, b = pr.shift_problem(n, 21)
     A = 0.5 * (A + A.T)
@@ -116,3 +116,30 @@ def test_declared_symmetric_reads_upper_block_triangle_only():
     import torch
     d = make_solver(pr.BBPGD, 1e-6, 400).solve(torch.from_numpy(A).cuda(), torch.from_numpy(b).cuda(), convex_proj_op=op, symmetric=True)
     assert np.array_equal(d.solution.cpu().numpy(), np.asarray(ref.solution))
+
+
+def test_pending_mirror_does_not_outlive_its_matrix():
+    """The mirror kernel of a symmetric host matrix is launched by the first user of the matrix; a matrix that is replaced
+    before it was ever used (here by a CSR Hessian of another size) must not be mirrored into the new one's buffers."""
+    import scipy.sparse as sp
+    n = 2304
+    A, b = pr.shift_problem(n, 2)
+    A = 0.5 * (A + A.T)
+    h = _capi.Handle(-1)
+    pa, mem, _ = _capi.f64_ptr(A)
+    _capi.check(h.h, h.lib.ccqp_set_matrix(h.h, pa, n, n, 0, n, mem))          # upload enqueued, mirror pending
+    assert h.upload_info()[1]
+    m = 3000
+    S = (sp.random(m, m, density=0.002, random_state=1, format="csr") + sp.identity(m) * 4.0).tocsr()
+    S = (S + S.T).tocsr()
+    S.sort_indices()
+    indptr = S.indptr.astype(np.int64); indices = S.indices.astype(np.int32); values = S.data.astype(np.float64)
+    _capi.check(h.h, h.lib.ccqp_set_matrix_csr(h.h, ctypes.c_void_p(indptr.ctypes.data), ctypes.c_void_p(indices.ctypes.data),
+                                               ctypes.c_void_p(values.ctypes.data), m, S.nnz, 0, m, _capi.MEM_HOST))
+    assert h.upload_info() == (0, False)
+    v = np.random.default_rng(0).standard_normal(m)
+    y = np.empty(m)
+    _capi.check(h.h, h.lib.ccqp_gemv(h.h, _capi.f64_ptr(v)[0], _capi.f64_ptr(y)[0], _capi.MEM_HOST))
+    ref = S @ v
+    assert np.abs(y - ref).max() <= 1e-12 * np.abs(ref).max()
+    h.close()
