@@ -12,6 +12,10 @@ from ccqppy_b200 import _capi
 
 pytestmark = pytest.mark.gpu
 
+# the host-side symmetry test (and with it the automatic half upload) runs only where the process has at least 12 hardware
+# threads (csrc/upload.cu); on a smaller host ccqp_set_matrix uploads every matrix whole
+AUTO = len(os.sched_getaffinity(0)) >= 12
+
 
 def upload_info():
     h = _capi.default_handle(-1)
@@ -44,9 +48,12 @@ def test_symmetric_matrix_uploads_upper_block_triangle(n):
     for solver in (pr.BBPGD, pr.SPG):
         x1, mv1, (bytes1, mir1) = solve_host(solver, A, b, tab, True)
         x0, mv0, (bytes0, mir0) = solve_host(solver, A, b, tab, False)
-        assert mir1 and not mir0
+        assert mir1 == AUTO and not mir0
         assert bytes0 == 8 * n * n
-        assert bytes1 == 8 * sum(min(B, n - i0) * (n - i0) for i0 in range(0, n, B)) < 0.8 * bytes0
+        if AUTO:
+            assert bytes1 == 8 * sum(min(B, n - i0) * (n - i0) for i0 in range(0, n, B)) < 0.8 * bytes0
+        else:
+            assert bytes1 == bytes0
         assert mv1 == mv0 and np.array_equal(x1, x0)          # the device copies are bit-identical
 
 
@@ -127,7 +134,7 @@ def test_pending_mirror_does_not_outlive_its_matrix():
     A = 0.5 * (A + A.T)
     h = _capi.Handle(-1)
     pa, mem, _ = _capi.f64_ptr(A)
-    _capi.check(h.h, h.lib.ccqp_set_matrix(h.h, pa, n, n, 0, n, mem))          # upload enqueued, mirror pending
+    _capi.check(h.h, h.lib.ccqp_set_matrix_symmetric(h.h, pa, n, n, mem))      # upload enqueued, mirror pending
     assert h.upload_info()[1]
     m = 3000
     S = (sp.random(m, m, density=0.002, random_state=1, format="csr") + sp.identity(m) * 4.0).tocsr()
