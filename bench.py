@@ -5,14 +5,17 @@
     python bench.py --impl reference --gpus N --steps K --warmup W   (CPU reference arm)
 
 Workload (BASELINE.json config 3): dense SPG-QP, n = 32768, fp64,
-A = G G^T / n + I (seed 0), b = -A x*, x* = 1 - 4 U, Box[-1,1]^n, tol 1e-5, max 2000 mat-vecs,
+A = G G^T / n + I (seed 0, symmetrised to the last bit), b = -A x*, x* = 1 - 4 U, Box[-1,1]^n, tol 1e-5, max 2000 mat-vecs,
 SPG uniforms = RandomState(0).  One "step" = one whole solve (about 56 mat-vecs, each streaming
 the 8.59 GB Hessian once).  metric = SPG iterations (= mat-vecs executed) per second.
 
   value : device-resident A (already in HBM), timed with CUDA events around the K solves
   e2e   : the same solves through the public API from pinned HOST buffers: the timed region
           includes the host->device copy of A, b, uniforms and the device->host copy of x
-          (`value` of e2e = a pipelined STREAM of solves, `one_at_a_time` = the plain loop)
+          (`value` of e2e = a pipelined STREAM of solves, `one_at_a_time` = the plain loop).  ccqp_set_matrix finds out
+          on the host, while the copy engine works, that this A is symmetric and moves only its upper block triangle
+          (`matrix_upload`, `h2d_bytes_per_step` = what actually crossed PCIe; the device copy is bit-identical to a full
+          upload); `declared_symmetric` = the same stream for a caller that declares the symmetry (no host-side test)
   roofline : algorithmic bytes of the solver kernel (mat-vecs x (8 n^2 + 16 n)) / its duration,
              against the measured HBM copy bandwidth in MEASURED_PEAKS.json
   parity : the solution / mat-vec count / converged flag of the timed solve against the CPU port of
@@ -21,7 +24,8 @@ the 8.59 GB Hessian once).  metric = SPG iterations (= mat-vecs executed) per se
   apgd  : config 3's second solver (CCQPSolverAPGD) on the same problem
   cpu_baseline : the NumPy/OpenBLAS port of the reference (oracle/) on this host's cores, the whole solve
   batched : config 4 (65536 box-QPs of n = 64, BBPGD and SPG) in the persistent per-CTA kernel, each
-            against max(HBM bytes / measured HBM peak, mat-vec flops / MEASURED fp64 peak)
+            against max(HBM bytes / measured HBM peak, mat-vec flops / MEASURED fp64 peak); `*_sym` = the same problems
+            through ccqp_solve_batched_sym (declared symmetric Hessians, one warp per problem)
   sparse : operator-form (CSR) Hessian, n = 2^20, ~57 stored entries per row (row f-3)
 
 With N > 1 (torchrun, one rank per GPU) A is row-sharded and the SAME problem is solved by all
