@@ -3,6 +3,7 @@
 #pragma once
 #include <algorithm>
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 #include <vector>
@@ -64,7 +65,8 @@ bool host_lower_blocks_mirror_upper(const double* A, long long n, long long lda,
     std::atomic<long long> next(0);
     std::atomic<bool> differs(false);
 #if CCQP_SYMCHECK_AVX2
-    const bool use_avx2 = __builtin_cpu_supports("avx2");
+    const char* scalar_env = getenv("CCQP_SYMCHECK_SCALAR");           // test hook: the portable path on an AVX2 machine
+    const bool use_avx2 = __builtin_cpu_supports("avx2") && !(scalar_env && atoi(scalar_env) != 0);
 #endif
     auto worker = [&]() {
         for (;;) {

@@ -13,6 +13,12 @@ def is_sym(A, threads=0):
     return _capi.load().ccqp_host_matrix_is_block_symmetric(ctypes.c_void_p(A.ctypes.data), A.shape[0], A.shape[1], threads)
 
 
+@pytest.fixture(params=["avx2", "scalar"], autouse=True)
+def code_path(request, monkeypatch):
+    """Every test runs through both inner loops of csrc/symcheck.h: the AVX2 4 x 4 transposes and the portable one."""
+    monkeypatch.setenv("CCQP_SYMCHECK_SCALAR", "1" if request.param == "scalar" else "0")
+
+
 def test_block_rows_constant():
     B = _capi.load().ccqp_upload_block_rows()
     assert B >= 64 and B % 32 == 0 and B % 4 == 0
@@ -79,3 +85,21 @@ def test_leading_dimension_and_bad_arguments():
     assert lib.ccqp_host_matrix_is_block_symmetric(ctypes.c_void_p(buf.ctypes.data), n, lda, 0) == 1
     assert lib.ccqp_host_matrix_is_block_symmetric(None, n, lda, 0) == -1
     assert lib.ccqp_host_matrix_is_block_symmetric(ctypes.c_void_p(buf.ctypes.data), n, n - 1, 0) == -1
+
+
+def test_random_single_entry_perturbations_property():
+    """Hypothesis-style sweep without the dependency: sizes that are and are not multiples of the 4 x 4 / 64 x 64 tiles, one
+    flipped mantissa bit at a random mirrored position, at a random thread count."""
+    B = _capi.load().ccqp_upload_block_rows()
+    rng = np.random.default_rng(2024)
+    for n in (B + 1, B + 3, B + 64, 2 * B + 5, 2 * B + 66, 3 * B - 1):
+        G = rng.standard_normal((n, n))
+        A = G + G.T
+        assert is_sym(A, threads=int(rng.integers(1, 9))) == 1
+        for _ in range(6):
+            i = int(rng.integers(B, n))
+            j = int(rng.integers(0, (i // B) * B))
+            C = A.copy()
+            bits = C[i:i + 1, j:j + 1].view(np.uint64)
+            bits ^= np.uint64(1) << np.uint64(int(rng.integers(0, 52)))
+            assert is_sym(C, threads=int(rng.integers(1, 9))) == 0, (n, i, j)

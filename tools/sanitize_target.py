@@ -35,3 +35,17 @@ for nb in (64, 17):
     for solver in range(7):
         make_solver(solver, 1e-7, 2000, 0.1).solve_batched(Ab, bb, -np.ones((B, nb)), np.ones((B, nb)))
 print("batched ok", flush=True)
+for nb in (64, 62, 17):      # the one-warp kernels for symmetric Hessians (staged and direct fills)
+    B = 40
+    Ab = np.empty((B, nb, nb)); bb = np.empty((B, nb))
+    for i in range(B):
+        Ab[i], bb[i] = pr.shift_problem(nb, i)
+    Ab = 0.5 * (Ab + Ab.transpose(0, 2, 1))
+    for solver in (pr.PGD, pr.BBPGD, pr.BBPGDF, pr.SPG):
+        make_solver(solver, 1e-7, 2000, 0.1).solve_batched(Ab, bb, -np.ones((B, nb)), np.ones((B, nb)), symmetric=True)
+print("batched symmetric ok", flush=True)
+for n2, declared in ((2100, False), (1500, True)):      # symmetric upload: upper block triangle + mirror kernel
+    A2, b2 = pr.shift_problem(n2, 3)
+    A2 = 0.5 * (A2 + A2.T)
+    make_solver(pr.BBPGD, 1e-6, 50).solve(A2, b2, convex_proj_op=op_from_table(pr.box_table(n2)), symmetric=declared)
+print("upload ok", flush=True)
